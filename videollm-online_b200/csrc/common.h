@@ -1,0 +1,63 @@
+// Host-side declarations shared by the translation units of libvlo_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace vlo {
+
+// ---- error plumbing: every C-ABI entry returns 0 / negative and leaves a message here.
+void set_error(const std::string& msg);
+const char* last_error();
+int fail(const std::string& msg);  // set_error + return -1
+
+#define VLO_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return ::vlo::fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" +    \
+                         __FILE__ + ":" + std::to_string(__LINE__));                    \
+  } while (0)
+
+#define VLO_CHECK(cond, msg)                                                            \
+  do {                                                                                  \
+    if (!(cond)) return ::vlo::fail(std::string("check failed: ") + #cond + ": " + msg); \
+  } while (0)
+
+#define VLO_LAUNCH_CHECK()                                                              \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess)                                                              \
+      return ::vlo::fail(std::string("kernel launch: ") + cudaGetErrorString(_e) + " @" + \
+                         __FILE__ + ":" + std::to_string(__LINE__));                    \
+  } while (0)
+
+// Launch counter (the bench reports how many of OUR kernels ran in the timed region).
+void count_launch(int n = 1);
+long long launch_count();
+
+// ---- GEMM (gemm.cu) ---------------------------------------------------------------
+struct GemmCall {
+  int fmt;   // 0 fp16, 1 bf16
+  int swap;  // 1: A = weights (MMA-M), B = tokens (MMA-N); logical out [rows_b, rows_a]
+  int epi;   // GemmEpi
+  int act;   // GemmAct
+  const void* a;
+  int rows_a;
+  const void* b;
+  int rows_b;
+  int k;
+  void* out;
+  int ld_out;
+  const float* bias;
+  const float* pos;
+  int pos_rows;
+  int splits;          // >1 only with EPI_PARTIAL; out is then the fp32 workspace
+  long long split_stride;
+  int stream_weights;  // 1: operand A is read once (EVICT_FIRST), B is hot (EVICT_LAST)
+  int bn;              // 0 = choose
+};
+int gemm_launch(const GemmCall& c, cudaStream_t stream);
+int gemm_fix_splits(int k, int want);
+
+}  // namespace vlo

@@ -1,0 +1,183 @@
+// Host launcher for the tcgen05 GEMM: TMA descriptor construction (driver entry point
+// resolved at run time, so the library loads on a box without libcuda), tile-shape
+// selection and kernel dispatch.
+#include "gemm.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.h"
+
+namespace vlo {
+
+namespace {
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                              CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int rows, k, box_rows, fmt;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && k == o.k && box_rows == o.box_rows && fmt == o.fmt;
+  }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& x) const {
+    size_t h = reinterpret_cast<size_t>(x.ptr);
+    h ^= (static_cast<size_t>(x.rows) * 0x9E3779B97F4A7C15ull) + (h << 6) + (h >> 2);
+    h ^= (static_cast<size_t>(x.k) * 0xC2B2AE3D27D4EB4Full) + (h << 6) + (h >> 2);
+    h ^= static_cast<size_t>(x.box_rows * 2 + x.fmt) + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapHash> g_tmaps;
+
+// [rows, k] row-major 16-bit matrix, box = 64 (k) x box_rows, 128-byte swizzle.
+int get_tmap(const void* ptr, int rows, int k, int box_rows, int fmt, CUtensorMap* out) {
+  TmapKey key{ptr, rows, k, box_rows, fmt};
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeFn enc = get_encode();
+  if (enc == nullptr) return fail("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail("TMA operand not 16-byte aligned");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(k) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, fmt == FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed, CUresult " + std::to_string(r));
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    g_tmaps.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
+template <int FMT, int BN, bool SWAP, int EPI>
+int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, dim3 grid,
+               cudaStream_t stream) {
+  auto kern = gemm_tn_kernel<FMT, BN, SWAP, EPI>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    VLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  GemmCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, args);
+  VLO_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+
+// Largest split count <= want for which every split owns at least one 64-wide k-block.
+int gemm_fix_splits(int k, int want) {
+  const int total_kb = k / kGemmBK;
+  int s = want < 1 ? 1 : (want > total_kb ? total_kb : want);
+  for (; s > 1; --s) {
+    const int per = (total_kb + s - 1) / s;
+    if ((total_kb + per - 1) / per == s) break;
+  }
+  return s;
+}
+
+int gemm_launch(const GemmCall& c, cudaStream_t stream) {
+  VLO_CHECK(c.k > 0 && c.k % kGemmBK == 0, "K must be a positive multiple of 64");
+  VLO_CHECK(c.rows_a > 0 && c.rows_b > 0, "empty GEMM operand");
+  VLO_CHECK(c.splits >= 1, "splits >= 1");
+  VLO_CHECK(c.splits == 1 || c.epi == EPI_PARTIAL, "split-K requires the fp32 partial epilogue");
+  const int total_kb = c.k / kGemmBK;
+  const int splits = c.splits > total_kb ? total_kb : c.splits;
+  const int kb_per = (total_kb + splits - 1) / splits;
+  const int eff_splits = (total_kb + kb_per - 1) / kb_per;  // every split gets >= 1 k-block
+  VLO_CHECK(eff_splits == c.splits, "split count leaves an empty split; use gemm_fix_splits()");
+
+  int bn = c.bn;
+  if (bn == 0) {
+    if (c.swap) bn = c.rows_b <= 16 ? 16 : (c.rows_b <= 32 ? 32 : (c.rows_b <= 64 ? 64 : 128));
+    else bn = 128;
+  }
+  GemmArgs a{};
+  a.rows_a = c.rows_a;
+  a.rows_b = c.rows_b;
+  a.k = c.k;
+  a.kb_per_split = kb_per;
+  a.out = c.out;
+  a.ld_out = c.ld_out;
+  a.bias = c.bias;
+  a.pos = c.pos;
+  a.pos_rows = c.pos_rows > 0 ? c.pos_rows : 1;
+  a.act = c.act;
+  a.split_stride = c.split_stride;
+  a.hint_a = c.stream_weights ? kEvictFirst : kEvictNormal;
+  a.hint_b = c.stream_weights ? kEvictLast : kEvictNormal;
+
+  CUtensorMap ta, tb;
+  if (get_tmap(c.a, c.rows_a, c.k, kGemmBM, c.fmt, &ta) != 0) return -1;
+  if (get_tmap(c.b, c.rows_b, c.k, bn, c.fmt, &tb) != 0) return -1;
+  dim3 grid((c.rows_a + kGemmBM - 1) / kGemmBM, (c.rows_b + bn - 1) / bn, eff_splits);
+
+#define VLO_GEMM_CASE(F, N, SW, E)                                                        \
+  if (c.fmt == F && bn == N && (c.swap != 0) == SW && c.epi == E)                         \
+    return launch_one<F, N, SW, E>(ta, tb, a, grid, stream);
+
+  // decoder / connector: bf16, swap-AB
+  VLO_GEMM_CASE(FMT_BF16, 16, true, EPI_PARTIAL)
+  VLO_GEMM_CASE(FMT_BF16, 32, true, EPI_PARTIAL)
+  VLO_GEMM_CASE(FMT_BF16, 64, true, EPI_PARTIAL)
+  VLO_GEMM_CASE(FMT_BF16, 128, true, EPI_PARTIAL)
+  VLO_GEMM_CASE(FMT_BF16, 16, true, EPI_STORE16)
+  VLO_GEMM_CASE(FMT_BF16, 32, true, EPI_STORE16)
+  VLO_GEMM_CASE(FMT_BF16, 64, true, EPI_STORE16)
+  VLO_GEMM_CASE(FMT_BF16, 128, true, EPI_STORE16)
+  // ViT MAP head (few rows): fp16, swap-AB
+  VLO_GEMM_CASE(FMT_F16, 16, true, EPI_STORE16)
+  VLO_GEMM_CASE(FMT_F16, 32, true, EPI_STORE16)
+  VLO_GEMM_CASE(FMT_F16, 64, true, EPI_STORE16)
+  VLO_GEMM_CASE(FMT_F16, 128, true, EPI_STORE16)
+  // ViT trunk: fp16, activations on MMA-M
+  VLO_GEMM_CASE(FMT_F16, 64, false, EPI_STORE16)
+  VLO_GEMM_CASE(FMT_F16, 128, false, EPI_STORE16)
+  VLO_GEMM_CASE(FMT_F16, 64, false, EPI_RESID32)
+  VLO_GEMM_CASE(FMT_F16, 128, false, EPI_RESID32)
+  VLO_GEMM_CASE(FMT_F16, 64, false, EPI_PATCH32)
+  VLO_GEMM_CASE(FMT_F16, 128, false, EPI_PATCH32)
+#undef VLO_GEMM_CASE
+  return fail("gemm_launch: no kernel instance for fmt=" + std::to_string(c.fmt) + " bn=" +
+              std::to_string(bn) + " swap=" + std::to_string(c.swap) + " epi=" + std::to_string(c.epi));
+}
+
+}  // namespace vlo
