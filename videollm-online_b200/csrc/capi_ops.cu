@@ -47,3 +47,36 @@ int vlo_op_gemm(int fmt, int swap, int epi, int act, const void* d_a, int rows_a
 }
 
 }  // extern "C"
+
+#include <vector>
+
+extern "C" {
+
+int64_t vlo_op_attn_ws_bytes(int n_tok, int n_heads, int head_dim, int kv_len) {
+  (void)head_dim;
+  (void)kv_len;
+  // n_kv_heads is not part of this query: bound it by n_heads (G = 1 is the worst case)
+  return 2 * static_cast<int64_t>(attn_ws_bytes(n_tok, 1, n_heads, n_heads));
+}
+
+int vlo_op_attn_kvappend(const void* d_q, const void* d_k, const void* d_v, void* d_out, float* d_ws, int n_tok,
+                         int n_heads, int n_kv_heads, int head_dim, int kv_len, long long kv_stride,
+                         void* cuda_stream) {
+  AttnSeq s{};
+  s.q_tok0 = 0;
+  s.q_len = n_tok;
+  s.kv_len = kv_len;
+  s.kv_row0 = 0;
+  s.kv_head_stride = static_cast<int>(kv_stride);
+  // the staging copy must outlive the async H2D: keep it in a per-thread buffer and sync the copy
+  static thread_local std::vector<uint8_t> stage;
+  stage.resize(attn_stage_bytes(n_tok, 1, n_heads, n_kv_heads));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  int rc = attn_launch(d_q, d_k, d_v, static_cast<long long>(n_kv_heads) * kv_stride, d_out, d_ws, stage.data(), &s,
+                       1, n_tok, n_heads, n_kv_heads, head_dim, st);
+  if (rc != 0) return rc;
+  VLO_CUDA(cudaStreamSynchronize(st));  // pageable staging buffer: make the copies complete before returning
+  return 0;
+}
+
+}  // extern "C"

@@ -60,4 +60,21 @@ struct GemmCall {
 int gemm_launch(const GemmCall& c, cudaStream_t stream);
 int gemm_fix_splits(int k, int want);
 
+// ---- attention (attn.cu) ------------------------------------------------------------
+struct AttnSeq {
+  int q_tok0;          // first packed token of the sequence
+  int q_len;           // new tokens
+  int kv_len;          // cache length INCLUDING the new tokens
+  long long kv_row0;   // row of (key 0, kv head 0) in the K / V matrices ([rows, head_dim])
+  int kv_head_stride;  // rows between kv heads
+};
+// bytes of scratch attn_launch needs for these sequences (upper bound)
+size_t attn_ws_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads);
+// d_k / d_v: [kv_rows, 128] bf16.  h_stage: pinned or pageable host scratch >= attn_stage_bytes(),
+// must stay untouched until the copy enqueued on `stream` has run.
+size_t attn_stage_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads);
+int attn_launch(const void* d_q, const void* d_k, const void* d_v, long long kv_rows, void* d_out,
+                void* d_ws, void* h_stage, const AttnSeq* seqs, int n_seqs, int total_tokens,
+                int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream);
+
 }  // namespace vlo

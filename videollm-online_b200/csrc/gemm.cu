@@ -103,6 +103,10 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& arg
 
 }  // namespace
 
+int tmap_2d_sw128(const void* ptr, int rows, int k, int box_rows, int fmt, CUtensorMap* out) {
+  return get_tmap(ptr, rows, k, box_rows, fmt, out);
+}
+
 // Largest split count <= want for which every split owns at least one 64-wide k-block.
 int gemm_fix_splits(int k, int want) {
   const int total_kb = k / kGemmBK;
