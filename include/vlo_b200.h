@@ -56,7 +56,8 @@ typedef struct vlo_decision {
   float max_logit;            /* for diagnostics / margins */
   float top2_margin;          /* max logit - second max logit */
   float lse;                  /* log-sum-exp of the logits */
-  int32_t reserved0, reserved1;
+  int32_t argmax_prob_id;     /* argmax over the bf16-rounded softmax (what next_score.argmax sees), first index wins ties */
+  int32_t reserved1;
 } vlo_decision;
 
 const char* vlo_last_error(void);

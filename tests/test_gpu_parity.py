@@ -1,0 +1,233 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference goldens and the CPU oracle.
+
+Tolerances (stated per north_star): the decoder computes in bf16 like the reference; differences come only
+from accumulation order inside GEMMs / attention, so last-position logits must agree within
+LOGIT_ATOL + LOGIT_RTOL*|x| and greedy ids must be identical wherever the oracle's top-1/top-2 margin
+exceeds 2*LOGIT_ATOL.  The ViT runs fp16 operands / fp32 accumulate (the reference's GPU autocast
+flow) against the fp32 CPU oracle: VIT_ATOL on tokens of O(1) magnitude."""
+import pathlib
+import sys
+
+import pytest
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "oracle"))
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ATOL, LOGIT_RTOL = 0.25, 0.02
+VIT_ATOL = 3e-2
+EMBED_ATOL = 6e-2
+
+
+@pytest.fixture(scope="module")
+def built(tiny):
+    from videollm_online_b200.modeling_live import build_live
+    cfg, llm, vis = tiny
+    model, tok = build_live(config=cfg, llm_state=llm, vision_state=vis, set_vision_inside=True, device="cuda:0",
+                            max_streams=4, max_kv_tokens=1024, max_step_tokens=64, max_vit_batch=4)
+    return model, tok
+
+
+def _close(a, b, atol, rtol):
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs()
+    bad = err > atol + rtol * b.abs()
+    return float(err.max()), float(bad.float().mean())
+
+
+def test_vit_tokens_vs_reference(built, golden):
+    model, _ = built
+    _, tok = model.engine.vit_encode(golden["frames"].cuda(), return_vit_tokens=True, connector=False)
+    ref = golden["vit_tokens"]
+    assert tok.shape == ref.shape
+    mx, frac = _close(tok, ref, VIT_ATOL, 2e-2)
+    assert frac == 0.0, f"vit tokens max err {mx}"
+
+
+def test_visual_embed_vs_reference(built, golden):
+    model, _ = built
+    out = model.visual_embed(golden["frames"].cuda())
+    ref = golden["visual_embed"]
+    assert out.shape == ref.shape and out.dtype == torch.bfloat16
+    mx, frac = _close(out, ref, EMBED_ATOL, 3e-2)
+    assert frac == 0.0, f"visual_embed max err {mx}"
+
+
+def test_connector_only_path(built, golden):
+    # visual_embed on pre-extracted features applies only the connector
+    import vlo_oracle as O
+    model, _ = built
+    out = model.visual_embed(golden["vit_tokens"].cuda())
+    mx, frac = _close(out, golden["visual_embed"], EMBED_ATOL, 3e-2)
+    assert frac == 0.0, mx
+
+
+def test_chunked_kv_append_logits_and_cache(built, golden, tiny):
+    cfg, _, _ = tiny
+    model, _ = built
+    eng = model.engine
+    kv = model.new_stream()
+    off, worst = 0, 0.0
+    ref_all = golden["step_logits"]
+    for c in golden["step_chunks"].tolist():
+        emb = golden["step_embeds"][off:off + c].cuda()
+        out = model(inputs_embeds=emb[None], past_key_values=kv, use_cache=True)
+        last = out.logits[0, 0]
+        mx, frac = _close(last, ref_all[off + c - 1], LOGIT_ATOL, LOGIT_RTOL)
+        assert frac == 0.0, f"chunk at {off}: last-logit max err {mx}"
+        allpos = eng.last_step_logits(c)
+        mx2, frac2 = _close(allpos, ref_all[off:off + c], LOGIT_ATOL, LOGIT_RTOL)
+        assert frac2 == 0.0, f"chunk at {off}: all-position max err {mx2}"
+        worst = max(worst, mx, mx2)
+        # greedy id exact wherever the oracle margin is healthy
+        dec = eng.read_decisions(1)[0]
+        top2 = ref_all[off + c - 1].float().topk(2).values
+        if float(top2[0] - top2[1]) > 2 * LOGIT_ATOL:
+            assert dec.argmax_id == int(ref_all[off + c - 1].float().argmax())
+        off += c
+    assert kv.get_seq_length() == 41
+    for layer, kk, vk in ((0, "kv_k0", "kv_v0"), (cfg.num_hidden_layers - 1, "kv_kL", "kv_vL")):
+        k, v = eng.kv_read(kv.stream_id, layer, False), eng.kv_read(kv.stream_id, layer, True)
+        assert _close(k, golden[kk], 4e-2, 2e-2)[1] == 0.0
+        assert _close(v, golden[vk], 4e-2, 2e-2)[1] == 0.0
+    eng.stream_close(kv.stream_id)
+
+
+def test_one_pass_equals_chunked(built, golden):
+    model, _ = built
+    kv = model.new_stream()
+    out = model(inputs_embeds=golden["step_embeds"].cuda()[None], past_key_values=kv, use_cache=True)
+    mx, frac = _close(out.logits[0, 0], golden["step_logits_onepass"][-1], LOGIT_ATOL, LOGIT_RTOL)
+    assert frac == 0.0, mx
+    model.engine.stream_close(kv.stream_id)
+
+
+def test_greedy_generate_ids_exact(built, golden, tiny):
+    from videollm_online_b200.modeling_live import fast_greedy_generate
+    cfg, _, _ = tiny
+    model, _ = built
+    kv = model.new_stream()
+    buf = torch.zeros(1, 12, dtype=torch.long)
+    ids, kv2 = fast_greedy_generate(model=model, inputs_embeds=golden["gen_prompt"].cuda()[None], past_key_values=kv,
+                                    eos_token_id=cfg.eos_token_id, inplace_output_ids=buf)
+    assert ids[0].tolist() == golden["gen_ids"].tolist()
+    assert kv2.get_seq_length() == 14 + len(golden["gen_ids"]) - 1 or ids[0, -1].item() == cfg.eos_token_id
+    model.engine.stream_close(kv.stream_id)
+
+
+def test_decision_kernel_matches_reference_rule(built, tiny):
+    import vlo_oracle as O
+    cfg, _, _ = tiny
+    model, _ = built
+    eng = model.engine
+    kv = model.new_stream()
+    g = torch.Generator().manual_seed(5)
+    for _ in range(4):
+        emb = torch.randn(11, cfg.hidden_size, generator=g).to(torch.bfloat16).cuda()
+        logits, _ = eng.step([kv.stream_id], [11], emb)
+        dec = eng.read_decisions(1)[0]
+        row = logits[0].float().cpu().to(torch.bfloat16)
+        for thr in (0.0, 0.3, 0.725, 1.0):
+            assert dec.next_id(cfg.frame_token_interval_id, thr) == O.decide(row.clone(), cfg.frame_token_interval_id, thr)
+        assert dec.argmax_id == int(row.float().argmax())
+        p = float(row.view(1, -1).softmax(-1)[0, cfg.frame_token_interval_id])
+        assert abs(dec.p_interval - p) <= 1e-2 * max(p, 1e-3) + 1e-6
+    eng.stream_close(kv.stream_id)
+
+
+def test_batched_streams_equal_single_stream(built, tiny):
+    """config 3/5: a ragged batch of independent streams gives each stream the logits it gets alone."""
+    cfg, _, _ = tiny
+    model, _ = built
+    eng = model.engine
+    g = torch.Generator().manual_seed(9)
+    lens = [11, 1, 17]
+    embs = [torch.randn(n, cfg.hidden_size, generator=g).to(torch.bfloat16).cuda() for n in lens]
+    pre = [torch.randn(n, cfg.hidden_size, generator=g).to(torch.bfloat16).cuda() for n in (30, 5, 64)]
+    solo = []
+    for e0, e1 in zip(pre, embs):
+        s = eng.stream_open()
+        eng.step([s], [e0.shape[0]], e0)
+        lg, _ = eng.step([s], [e1.shape[0]], e1)
+        solo.append(lg[0].clone())
+        eng.stream_close(s)
+    sids = [eng.stream_open() for _ in lens]
+    eng.step(sids, [e.shape[0] for e in pre], torch.cat(pre, 0))
+    lg, _ = eng.step(sids, lens, torch.cat(embs, 0))
+    for i in range(3):
+        assert torch.equal(lg[i], solo[i]), float((lg[i].float() - solo[i].float()).abs().max())
+    assert [eng.kv_len(s) for s in sids] == [41, 6, 81]
+    for s in sids:
+        eng.stream_close(s)
+
+
+def test_state_machine_vs_reference_liveinfer(built, golden, tiny):
+    """LiveInfer over the engine reproduces the trace of the reference's LiveInfer methods (scripted decisions)."""
+    from videollm_online_b200.config import LiveArguments, SYSTEM_PROMPT
+    from videollm_online_b200.inference import LiveInfer
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    from make_golden import golden_schedule
+    cfg, _, _ = tiny
+    model, tok = built
+    sched = golden_schedule(cfg)
+
+    def hook(dec, call):
+        t = sched.get(call)
+        if t is not None:
+            dec.argmax_id = dec.argmax_prob_id = t
+            dec.p_interval = 1.0 if t == cfg.frame_token_interval_id else 0.0
+            if t != cfg.frame_token_interval_id:
+                dec.argmax_excl_id = t
+        return dec
+
+    li = LiveInfer(LiveArguments(frame_fps=2, system_prompt=SYSTEM_PROMPT), model=model, tokenizer=tok)
+    li.decision_hook = hook
+    li.load_video(golden["sm_video"])
+    trace = []
+    for i in range(8):
+        li.input_video_stream(i / 2)
+        query, response = li()
+        trace.append((i, query, response, int(li.last_ids.reshape(-1)[-1]), li.past_key_values.get_seq_length()))
+    ref = golden["sm_trace"]
+    # kv accounting, decisions and scripted ids must match exactly; the two natural tokens of the first
+    # response come from near-tied random logits, so the response TEXT is compared only for the scripted parts
+    assert [(t[0], t[1], t[3], t[4]) for t in trace] == [(t[0], t[1], t[3], t[4]) for t in ref]
+    assert li._n_calls == golden["sm_calls"]
+
+
+def test_kv_truncate_and_reset(built, tiny):
+    cfg, _, _ = tiny
+    model, _ = built
+    eng = model.engine
+    s = eng.stream_open()
+    g = torch.Generator().manual_seed(2)
+    a = torch.randn(20, cfg.hidden_size, generator=g).to(torch.bfloat16).cuda()
+    b = torch.randn(5, cfg.hidden_size, generator=g).to(torch.bfloat16).cuda()
+    eng.step([s], [20], a)
+    l1 = eng.step([s], [5], b)[0][0].clone()
+    eng.kv_truncate(s, 20)
+    assert eng.kv_len(s) == 20
+    l2 = eng.step([s], [5], b)[0][0].clone()
+    assert torch.equal(l1, l2)
+    eng.stream_reset(s)
+    assert eng.kv_len(s) == 0 and not bool(__import__("videollm_online_b200").modeling_live.StreamKV(eng, s))
+    with pytest.raises(Exception):
+        eng.kv_truncate(s, 3)
+    eng.stream_close(s)
+
+
+def test_error_paths(built, tiny):
+    from videollm_online_b200 import VloError
+    cfg, _, _ = tiny
+    model, _ = built
+    eng = model.engine
+    with pytest.raises(VloError):
+        eng.step([99], [1], torch.zeros(1, cfg.hidden_size, dtype=torch.bfloat16, device="cuda"))
+    s = eng.stream_open()
+    with pytest.raises(VloError):  # exceeds max_step_tokens
+        eng.step([s], [65], torch.zeros(65, cfg.hidden_size, dtype=torch.bfloat16, device="cuda"))
+    with pytest.raises(VloError):
+        eng.vit_encode(torch.zeros(1, 3, 32, 32, dtype=torch.uint8))
+    eng.stream_close(s)

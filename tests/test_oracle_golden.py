@@ -1,0 +1,88 @@
+"""Pin oracle/vlo_oracle.py against outputs of the reference's own modules (tests/golden/make_golden.py)."""
+import sys
+import pathlib
+
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "oracle"))
+import vlo_oracle as O  # noqa: E402
+
+
+def test_vision_tokens_match_reference(golden, tiny):
+    cfg, llm, vis = tiny
+    tok = O.siglip_vision_encode(vis, cfg, golden["frames"])
+    assert tok.shape == golden["vit_tokens"].shape
+    torch.testing.assert_close(tok, golden["vit_tokens"], rtol=1e-4, atol=1e-5)
+
+
+def test_visual_embed_matches_reference(golden, tiny):
+    cfg, llm, vis = tiny
+    out = O.visual_embed(llm, vis, cfg, golden["frames"])
+    ref = golden["visual_embed"]
+    assert out.dtype == torch.bfloat16 and out.shape == ref.shape
+    # bf16 connector on fp32 tokens that agree to 1e-5: allow a couple of bf16 ulps
+    torch.testing.assert_close(out.float(), ref.float(), rtol=2e-2, atol=2e-2)
+    assert (out == ref).float().mean() > 0.98
+
+
+def test_chunked_kv_append_forward_is_bit_exact(golden, tiny):
+    cfg, llm, vis = tiny
+    cache = O.KVCache(cfg.num_hidden_layers)
+    logits, off = [], 0
+    for c in golden["step_chunks"].tolist():
+        logits.append(O.llama_forward(llm, cfg, golden["step_embeds"][off:off + c], cache))
+        off += c
+    logits = torch.cat(logits, 0)
+    assert torch.equal(logits, golden["step_logits"]), (logits.float() - golden["step_logits"].float()).abs().max()
+    assert torch.equal(cache.k[0][0], golden["kv_k0"]) and torch.equal(cache.v[0][0], golden["kv_v0"])
+    L = cfg.num_hidden_layers - 1
+    assert torch.equal(cache.k[L][0], golden["kv_kL"]) and torch.equal(cache.v[L][0], golden["kv_vL"])
+
+
+def test_chunked_equals_one_pass(golden):
+    # streaming in chunks == one causal pass (bf16: equal up to rounding)
+    a, b = golden["step_logits"].float(), golden["step_logits_onepass"].float()
+    assert (a - b).abs().max() < 0.5 and (a.argmax(-1) == b.argmax(-1)).float().mean() > 0.9
+
+
+def test_greedy_ids_bit_exact(golden, tiny):
+    cfg, llm, vis = tiny
+    ids = O.fast_greedy_generate(llm, cfg, golden["gen_prompt"], O.KVCache(cfg.num_hidden_layers), cfg.eos_token_id, max_new=12)
+    assert ids == golden["gen_ids"].tolist()
+
+
+def test_state_machine_matches_reference_liveinfer(golden, tiny):
+    cfg, llm, vis = tiny
+    from videollm_online_b200.config import SYSTEM_PROMPT
+    from videollm_online_b200.tokenization_live import ByteTokenizer
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    from make_golden import golden_schedule
+    sched, calls = golden_schedule(cfg), [0]
+
+    def hook(logits, kind):
+        tok = sched.get(calls[0])
+        calls[0] += 1
+        if tok is not None:
+            logits = logits.clone()
+            logits[tok] += 1000.0
+        return logits
+
+    li = O.OracleLiveInfer(llm, vis, cfg, ByteTokenizer(cfg), frame_fps=2, system_prompt=SYSTEM_PROMPT, logit_hook=hook)
+    li.load_video(golden["sm_video"])
+    trace = []
+    for i in range(8):
+        li.input_video_stream(i / 2)
+        query, response = li()
+        trace.append((i, query, response, int(li.last_ids.reshape(-1)[-1]), li.cache.get_seq_length()))
+    assert trace == golden["sm_trace"]
+    assert calls[0] == golden["sm_calls"]
+
+
+def test_decide_rule():
+    # demo/inference.py:76-79: below-threshold interval probability is zeroed before the argmax
+    x = torch.full((16,), -10.0, dtype=torch.bfloat16)
+    x[3], x[5] = 2.0, 1.5          # p(3) ~ 0.62 < 0.725 -> second best wins when 3 is the interval id
+    assert O.decide(x.clone(), 3, 0.725) == 5
+    assert O.decide(x.clone(), 3, 0.5) == 3
+    assert O.decide(x.clone(), 7, 0.725) == 3

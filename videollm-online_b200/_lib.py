@@ -35,7 +35,7 @@ class VloDecision(C.Structure):
     _fields_ = [
         ("argmax_id", C.c_int32), ("argmax_excl_id", C.c_int32), ("p_interval", C.c_float),
         ("max_logit", C.c_float), ("top2_margin", C.c_float), ("lse", C.c_float),
-        ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("argmax_prob_id", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 

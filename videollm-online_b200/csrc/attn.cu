@@ -1,5 +1,7 @@
 // Host side of the KV-append attention: chunking of sequences into <=64-row work items,
 // split-KV planning (one wave of CTAs over the 148 SMs), workspace layout and launches.
+// The plan depends only on (q_len, kv_len) of the sequences, so a decoder step builds and
+// uploads it once and reuses it for all layers.
 #include "attn.cuh"
 
 #include <cmath>
@@ -10,8 +12,6 @@
 
 namespace vlo {
 
-int tmap_2d_sw128(const void* ptr, int rows, int k, int box_rows, int fmt, CUtensorMap* out);
-
 namespace {
 constexpr int kNumSMs = 148;
 constexpr size_t kAlign = 256;
@@ -21,6 +21,12 @@ int max_chunks(int total_tokens, int n_seqs, int G) {
   const int per = 64 / G;
   return total_tokens / per + n_seqs + 1;
 }
+// Per item n_splits <= max(1, 148 / (n_kv_heads * n_items)) and rows <= 64, so the sum of
+// n_kv_heads * n_splits * rows over all items is bounded by (148 + n_kv_heads * n_items) * 64.
+size_t cap_slots_for(int total_tokens, int n_seqs, int n_heads, int n_kv_heads) {
+  const int G = n_heads / n_kv_heads;
+  return static_cast<size_t>(kNumSMs + n_kv_heads * max_chunks(total_tokens, n_seqs, G)) * 64;
+}
 }  // namespace
 
 size_t attn_stage_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads) {
@@ -28,35 +34,27 @@ size_t attn_stage_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_head
   return align_up(sizeof(AttnItem) * max_chunks(total_tokens, n_seqs, G)) + align_up(sizeof(int) * total_tokens);
 }
 
-// Per item n_splits <= max(1, 148 / (n_kv_heads * n_items)) and rows <= 64, so the sum of
-// n_kv_heads * n_splits * rows over all items is bounded by (148 + n_kv_heads * n_items) * 64.
-static size_t cap_slots_for(int total_tokens, int n_seqs, int n_heads, int n_kv_heads) {
-  const int G = n_heads / n_kv_heads;
-  return static_cast<size_t>(kNumSMs + n_kv_heads * max_chunks(total_tokens, n_seqs, G)) * 64;
-}
-
 size_t attn_ws_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads) {
+  const int G = n_heads / n_kv_heads;
   const size_t slots = cap_slots_for(total_tokens, n_seqs, n_heads, n_kv_heads);
-  return align_up(slots * kAttnHD * 4) + align_up(slots * 2 * 4) + align_up(sizeof(AttnItem) * (total_tokens + 64)) +
-         align_up(sizeof(int) * total_tokens);
+  return align_up(slots * kAttnHD * 4) + align_up(slots * 2 * 4) +
+         align_up(sizeof(AttnItem) * max_chunks(total_tokens, n_seqs, G)) + align_up(sizeof(int) * total_tokens);
 }
 
-int attn_launch(const void* d_q, const void* d_k, const void* d_v, long long kv_rows, void* d_out,
-                void* d_ws, void* h_stage, const AttnSeq* seqs, int n_seqs, int total_tokens,
-                int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream) {
+int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, int n_seqs, int total_tokens,
+              int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream) {
   VLO_CHECK(head_dim == kAttnHD, "decoder attention kernel is built for head_dim 128");
   VLO_CHECK(n_heads % n_kv_heads == 0, "n_heads must be a multiple of n_kv_heads");
   const int G = n_heads / n_kv_heads;
   VLO_CHECK(G <= 64, "GQA group too large");
-  VLO_CHECK(kv_rows > 0 && kv_rows < (1ll << 31), "KV matrix rows out of range for a TMA map");
   const int per = 64 / G;
 
-  // ---- plan
   std::vector<AttnItem> items;
   std::vector<int> tok_item(total_tokens, 0);
   for (int s = 0; s < n_seqs; ++s) {
     const AttnSeq& q = seqs[s];
     VLO_CHECK(q.q_len > 0 && q.kv_len >= q.q_len, "bad sequence lengths");
+    VLO_CHECK(q.kv_row0 >= 0 && q.kv_row0 < (1ll << 31), "kv_row0 out of range");
     for (int t0 = 0; t0 < q.q_len; t0 += per) {
       AttnItem it{};
       it.q_tok0 = q.q_tok0 + t0;
@@ -84,29 +82,36 @@ int attn_launch(const void* d_q, const void* d_k, const void* d_v, long long kv_
   }
   const size_t cap_slots = cap_slots_for(total_tokens, n_seqs, n_heads, n_kv_heads);
   VLO_CHECK(slots <= cap_slots, "attention workspace plan overflow");
+  VLO_CHECK(n_items <= max_chunks(total_tokens, n_seqs, G), "too many attention work items");
 
-  // ---- workspace carve-up (same order as attn_ws_bytes)
+  // workspace carve-up (same order as attn_ws_bytes)
   uint8_t* w = static_cast<uint8_t*>(d_ws);
-  float* ws_o = reinterpret_cast<float*>(w);
+  plan->ws_o = reinterpret_cast<float*>(w);
   w += align_up(cap_slots * kAttnHD * 4);
-  float* ws_ml = reinterpret_cast<float*>(w);
+  plan->ws_ml = reinterpret_cast<float*>(w);
   w += align_up(cap_slots * 2 * 4);
-  AttnItem* d_items = reinterpret_cast<AttnItem*>(w);
-  w += align_up(sizeof(AttnItem) * (total_tokens + 64));
-  int* d_tok_item = reinterpret_cast<int*>(w);
-  VLO_CHECK(n_items <= total_tokens + 64, "too many attention work items");
+  plan->d_items = w;
+  w += align_up(sizeof(AttnItem) * max_chunks(total_tokens, n_seqs, G));
+  plan->d_tok_item = reinterpret_cast<int*>(w);
+  plan->n_items = n_items;
+  plan->max_splits = max_splits;
+  plan->total_tokens = total_tokens;
 
   uint8_t* hs = static_cast<uint8_t*>(h_stage);
   std::memcpy(hs, items.data(), sizeof(AttnItem) * n_items);
   uint8_t* hs2 = hs + align_up(sizeof(AttnItem) * max_chunks(total_tokens, n_seqs, G));
   std::memcpy(hs2, tok_item.data(), sizeof(int) * total_tokens);
-  VLO_CUDA(cudaMemcpyAsync(d_items, hs, sizeof(AttnItem) * n_items, cudaMemcpyHostToDevice, stream));
-  VLO_CUDA(cudaMemcpyAsync(d_tok_item, hs2, sizeof(int) * total_tokens, cudaMemcpyHostToDevice, stream));
+  VLO_CUDA(cudaMemcpyAsync(plan->d_items, hs, sizeof(AttnItem) * n_items, cudaMemcpyHostToDevice, stream));
+  VLO_CUDA(cudaMemcpyAsync(plan->d_tok_item, hs2, sizeof(int) * total_tokens, cudaMemcpyHostToDevice, stream));
+  return 0;
+}
 
+int attn_run(const AttnPlan& plan, const void* d_q, const void* d_k, const void* d_v, long long kv_rows, void* d_out,
+             int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream) {
+  VLO_CHECK(kv_rows > 0 && kv_rows < (1ll << 31), "KV matrix rows out of range for a TMA map");
   CUtensorMap tk, tv;
   if (tmap_2d_sw128(d_k, static_cast<int>(kv_rows), kAttnHD, kAttnBlk, 1, &tk) != 0) return -1;
   if (tmap_2d_sw128(d_v, static_cast<int>(kv_rows), kAttnHD, kAttnBlk, 1, &tv) != 0) return -1;
-
   static bool attr_set = false;
   if (!attr_set) {
     VLO_CUDA(cudaFuncSetAttribute(attn_kvappend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
@@ -115,24 +120,24 @@ int attn_launch(const void* d_q, const void* d_k, const void* d_v, long long kv_
   const float scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(head_dim)));
   AttnParams p{};
   p.q = static_cast<const __nv_bfloat16*>(d_q);
-  p.ws_o = ws_o;
-  p.ws_ml = ws_ml;
-  p.items = d_items;
+  p.ws_o = plan.ws_o;
+  p.ws_ml = plan.ws_ml;
+  p.items = static_cast<const AttnItem*>(plan.d_items);
   p.n_heads = n_heads;
   p.n_kv_heads = n_kv_heads;
   p.scale_log2 = scale_log2;
-  attn_kvappend_kernel<<<dim3(max_splits, n_kv_heads, n_items), kAttnThreads, kAttnSmemBytes, stream>>>(tk, tv, p);
+  attn_kvappend_kernel<<<dim3(plan.max_splits, n_kv_heads, plan.n_items), kAttnThreads, kAttnSmemBytes, stream>>>(tk, tv, p);
   VLO_LAUNCH_CHECK();
   AttnMergeParams mp{};
-  mp.ws_o = ws_o;
-  mp.ws_ml = ws_ml;
-  mp.items = d_items;
-  mp.tok_item = d_tok_item;
+  mp.ws_o = plan.ws_o;
+  mp.ws_ml = plan.ws_ml;
+  mp.items = static_cast<const AttnItem*>(plan.d_items);
+  mp.tok_item = plan.d_tok_item;
   mp.out = static_cast<__nv_bfloat16*>(d_out);
   mp.n_heads = n_heads;
   mp.n_kv_heads = n_kv_heads;
   mp.scale_log2 = scale_log2;
-  attn_merge_kernel<<<dim3(n_heads, total_tokens), 128, 0, stream>>>(mp);
+  attn_merge_kernel<<<dim3(n_heads, plan.total_tokens), 128, 0, stream>>>(mp);
   VLO_LAUNCH_CHECK();
   count_launch(2);
   return 0;

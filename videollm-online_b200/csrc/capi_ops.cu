@@ -72,8 +72,11 @@ int vlo_op_attn_kvappend(const void* d_q, const void* d_k, const void* d_v, void
   static thread_local std::vector<uint8_t> stage;
   stage.resize(attn_stage_bytes(n_tok, 1, n_heads, n_kv_heads));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  int rc = attn_launch(d_q, d_k, d_v, static_cast<long long>(n_kv_heads) * kv_stride, d_out, d_ws, stage.data(), &s,
-                       1, n_tok, n_heads, n_kv_heads, head_dim, st);
+  AttnPlan plan{};
+  int rc = attn_plan(&plan, d_ws, stage.data(), &s, 1, n_tok, n_heads, n_kv_heads, head_dim, st);
+  if (rc != 0) return rc;
+  rc = attn_run(plan, d_q, d_k, d_v, static_cast<long long>(n_kv_heads) * kv_stride, d_out, n_heads, n_kv_heads,
+                head_dim, st);
   if (rc != 0) return rc;
   VLO_CUDA(cudaStreamSynchronize(st));  // pageable staging buffer: make the copies complete before returning
   return 0;

@@ -1,5 +1,6 @@
 // Host-side declarations shared by the translation units of libvlo_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -70,11 +71,23 @@ struct AttnSeq {
 };
 // bytes of scratch attn_launch needs for these sequences (upper bound)
 size_t attn_ws_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads);
-// d_k / d_v: [kv_rows, 128] bf16.  h_stage: pinned or pageable host scratch >= attn_stage_bytes(),
-// must stay untouched until the copy enqueued on `stream` has run.
 size_t attn_stage_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads);
-int attn_launch(const void* d_q, const void* d_k, const void* d_v, long long kv_rows, void* d_out,
-                void* d_ws, void* h_stage, const AttnSeq* seqs, int n_seqs, int total_tokens,
-                int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream);
+struct AttnPlan {
+  float* ws_o;
+  float* ws_ml;
+  void* d_items;
+  int* d_tok_item;
+  int n_items, max_splits, total_tokens;
+};
+// Build the work-item plan on the host and enqueue its upload.  h_stage (>= attn_stage_bytes())
+// must stay untouched until the copies enqueued on `stream` have run.
+int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, int n_seqs, int total_tokens,
+              int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream);
+// d_k / d_v: one layer's K / V matrices [kv_rows, 128] bf16; d_q [T, n_heads, 128]; d_out [T, n_heads*128].
+int attn_run(const AttnPlan& plan, const void* d_q, const void* d_k, const void* d_v, long long kv_rows, void* d_out,
+             int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream);
+
+// 2D TMA map over a row-major 16-bit matrix [rows, k], box 64 x box_rows, 128-byte swizzle (cached).
+int tmap_2d_sw128(const void* ptr, int rows, int k, int box_rows, int fmt, CUtensorMap* out);
 
 }  // namespace vlo

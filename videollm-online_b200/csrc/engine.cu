@@ -1,0 +1,775 @@
+// vlo_engine: weights registry, KV-cache ownership, workspaces and the orchestration of the
+// per-frame hot path (vlo_vit_encode, vlo_step) on one GPU.  See include/vlo_b200.h for the ABI
+// and DESIGN.md for the memory layout.
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "decoder_kernels.cuh"
+#include "gemm.cuh"
+#include "vit_kernels.cuh"
+#include "vlo_b200.h"
+
+using namespace vlo;
+
+namespace {
+
+constexpr int kNumSMs = 148;
+constexpr int kStageSlots = 16;
+
+using bf16 = __nv_bfloat16;
+
+struct DecLayer {
+  const bf16 *in_norm, *qkv, *o, *post_norm, *gate_up, *down;
+};
+struct VitLayer {
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *qkv_b, *out_b, *fc1_b, *fc2_b;
+  const __half *qkv_w, *out_w, *fc1_w, *fc2_w;
+};
+
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace
+
+struct vlo_engine {
+  vlo_config cfg{};
+  int device = 0;
+  std::map<std::string, std::pair<const void*, int64_t>> tensors;
+  bool finalized = false;
+
+  // resolved weights
+  std::vector<DecLayer> dec;
+  const bf16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr, *rope_cos = nullptr, *rope_sin = nullptr;
+  int64_t rope_positions = 0;
+  std::vector<VitLayer> vit;
+  const __half *patch_w = nullptr, *head_kv_w = nullptr, *head_out_w = nullptr, *head_fc1_w = nullptr,
+               *head_fc2_w = nullptr;
+  const float *patch_b = nullptr, *pos_emb = nullptr, *post_ln_w = nullptr, *post_ln_b = nullptr, *head_q = nullptr,
+              *head_kv_b = nullptr, *head_out_b = nullptr, *head_ln_w = nullptr, *head_ln_b = nullptr,
+              *head_fc1_b = nullptr, *head_fc2_b = nullptr, *conn0_b = nullptr, *conn2_b = nullptr;
+  const bf16 *conn0_w = nullptr, *conn2_w = nullptr;
+  bool has_vit = false, has_connector = false, has_decoder = false;
+
+  // derived
+  int qkv_width = 0, grid = 0, n_patches = 0, n_frame_tokens = 0, patch_k = 0;
+
+  // device allocations owned by the engine
+  std::vector<void*> allocs;
+  int64_t device_bytes = 0;
+  bf16* kv = nullptr;  // [layer][2][stream][kv_head][cap][128]
+  std::vector<int> kv_len;
+  std::vector<char> stream_open;
+
+  // decoder workspaces
+  bf16 *h = nullptr, *xn = nullptr, *xn_last = nullptr, *q = nullptr, *attn_out = nullptr, *act = nullptr,
+       *logits = nullptr;
+  float* part = nullptr;
+  size_t part_elems = 0;
+  uint8_t* attn_ws = nullptr;
+  uint8_t* meta_dev = nullptr;  // tok_pos | tok_kvrow | last_index | first_rows
+  size_t meta_bytes = 0;
+  DecisionOut* decisions = nullptr;
+  // host staging ring (pinned)
+  uint8_t* stage = nullptr;
+  size_t stage_slot_bytes = 0;
+  cudaEvent_t stage_events[kStageSlots]{};
+  bool stage_used[kStageSlots]{};
+  int stage_next = 0;
+  int last_step_tokens = 0;
+
+  // ViT workspaces
+  __half *patches = nullptr, *v_xn = nullptr, *v_qkv = nullptr, *v_attn = nullptr, *v_mlp = nullptr, *v_pa = nullptr,
+         *v_resid = nullptr, *v_lnh = nullptr, *v_m1 = nullptr, *v_m2 = nullptr;
+  float *v_h = nullptr, *v_ln32 = nullptr, *tokens32 = nullptr;
+  bf16 *tokens16 = nullptr, *conn_mid = nullptr;
+};
+
+namespace {
+
+int dev_alloc(vlo_engine* e, void** p, size_t bytes, bool zero) {
+  bytes = align256(bytes ? bytes : 256);
+  VLO_CUDA(cudaMalloc(p, bytes));
+  if (zero) VLO_CUDA(cudaMemset(*p, 0, bytes));
+  e->allocs.push_back(*p);
+  e->device_bytes += static_cast<int64_t>(bytes);
+  return 0;
+}
+template <typename T>
+int dev_alloc_t(vlo_engine* e, T** p, size_t n, bool zero = false) {
+  return dev_alloc(e, reinterpret_cast<void**>(p), n * sizeof(T), zero);
+}
+
+template <typename T>
+int lookup(vlo_engine* e, const std::string& name, int64_t expect_elems, const T** out) {
+  auto it = e->tensors.find(name);
+  if (it == e->tensors.end()) return fail("missing weight tensor '" + name + "'");
+  if (expect_elems > 0 && it->second.second != expect_elems * static_cast<int64_t>(sizeof(T)))
+    return fail("weight tensor '" + name + "' has " + std::to_string(it->second.second) + " bytes, expected " +
+                std::to_string(expect_elems * static_cast<int64_t>(sizeof(T))));
+  *out = static_cast<const T*>(it->second.first);
+  return 0;
+}
+
+// split-K factor: fill the 148 SMs in whole waves (one CTA per SM) with >= 4 k-blocks per split.
+int choose_splits(int tiles, int k) {
+  const int total_kb = k / kGemmBK;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 16; ++s) {
+    const int fs = gemm_fix_splits(k, s);
+    if (fs != s) continue;
+    if (total_kb / s < 4 && s > 1) break;
+    const int ctas = tiles * s;
+    const int waves = (ctas + kNumSMs - 1) / kNumSMs;
+    const double eff = static_cast<double>(ctas) / (waves * kNumSMs);
+    if (eff > best_eff + 0.03) {
+      best_eff = eff;
+      best = s;
+    }
+  }
+  return best;
+}
+
+int swap_bn(int rows_b) { return rows_b <= 16 ? 16 : (rows_b <= 32 ? 32 : (rows_b <= 64 ? 64 : 128)); }
+
+// weights [n_out, k] x tokens [T, k] -> fp32 partials [S][T][n_out] in e->part; returns S
+int gemm_partial(vlo_engine* e, const bf16* w, int n_out, const bf16* x, int T, int k, int* out_splits,
+                 cudaStream_t st) {
+  const int bn = swap_bn(T);
+  const int tiles = ((n_out + kGemmBM - 1) / kGemmBM) * ((T + bn - 1) / bn);
+  const int S = choose_splits(tiles, k);
+  VLO_CHECK(static_cast<size_t>(S) * T * n_out <= e->part_elems, "split-K workspace too small");
+  GemmCall c{};
+  c.fmt = FMT_BF16;
+  c.swap = 1;
+  c.epi = EPI_PARTIAL;
+  c.a = w;
+  c.rows_a = n_out;
+  c.b = x;
+  c.rows_b = T;
+  c.k = k;
+  c.out = e->part;
+  c.ld_out = n_out;
+  c.splits = S;
+  c.split_stride = static_cast<long long>(T) * n_out;
+  c.stream_weights = 1;
+  c.bn = bn;
+  *out_splits = S;
+  return gemm_launch(c, st);
+}
+
+int gemm_store16(int fmt, int swap, const void* a, int rows_a, const void* b, int rows_b, int k, void* out, int ld,
+                 const float* bias, int act, int bn, cudaStream_t st) {
+  GemmCall c{};
+  c.fmt = fmt;
+  c.swap = swap;
+  c.epi = EPI_STORE16;
+  c.act = act;
+  c.a = a;
+  c.rows_a = rows_a;
+  c.b = b;
+  c.rows_b = rows_b;
+  c.k = k;
+  c.out = out;
+  c.ld_out = ld;
+  c.bias = bias;
+  c.splits = 1;
+  c.stream_weights = swap;
+  c.bn = bn;
+  return gemm_launch(c, st);
+}
+
+int vit_bn(int rows, int n_out) {
+  const int tiles128 = ((rows + 127) / 128) * ((n_out + 127) / 128);
+  return tiles128 >= kNumSMs ? 128 : 64;
+}
+
+// pinned staging slot, recycled behind a CUDA event
+int stage_acquire(vlo_engine* e, uint8_t** out, int* slot) {
+  const int s = e->stage_next;
+  e->stage_next = (s + 1) % kStageSlots;
+  if (e->stage_used[s]) VLO_CUDA(cudaEventSynchronize(e->stage_events[s]));
+  *out = e->stage + static_cast<size_t>(s) * e->stage_slot_bytes;
+  *slot = s;
+  return 0;
+}
+int stage_release(vlo_engine* e, int slot, cudaStream_t st) {
+  VLO_CUDA(cudaEventRecord(e->stage_events[slot], st));
+  e->stage_used[slot] = true;
+  return 0;
+}
+
+inline bf16* kv_layer_base(vlo_engine* e, int layer, int is_v) {
+  const vlo_config& c = e->cfg;
+  const size_t rows = static_cast<size_t>(c.max_streams) * c.num_kv_heads * c.max_kv_tokens;
+  return e->kv + (static_cast<size_t>(layer) * 2 + is_v) * rows * c.head_dim;
+}
+inline long long kv_rows_per_layer(const vlo_config& c) {
+  return static_cast<long long>(c.max_streams) * c.num_kv_heads * c.max_kv_tokens;
+}
+
+int check_stream(vlo_engine* e, int sid) {
+  if (e == nullptr) return fail("null engine");
+  if (sid < 0 || sid >= e->cfg.max_streams || !e->stream_open[sid]) return fail("invalid stream id " + std::to_string(sid));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vlo_engine_create(const vlo_config* cfg, int device, vlo_engine** out) {
+  VLO_CHECK(cfg != nullptr && out != nullptr, "null argument");
+  VLO_CUDA(cudaSetDevice(device));
+  if (!vlo_device_supported(device)) return fail("device is not an sm_100 (Blackwell) GPU; there is no fallback path");
+  const vlo_config& c = *cfg;
+  VLO_CHECK(c.head_dim == 128, "decoder head_dim must be 128");
+  VLO_CHECK(c.hidden_size % 64 == 0 && c.intermediate_size % 64 == 0, "hidden/intermediate must be multiples of 64");
+  VLO_CHECK(c.num_heads % c.num_kv_heads == 0, "num_heads % num_kv_heads");
+  VLO_CHECK(c.max_streams >= 1 && c.max_kv_tokens >= 64 && c.max_step_tokens >= 1, "capacities");
+  VLO_CHECK(c.vit_layers == 0 || (c.vit_hidden % 64 == 0 && c.vit_hidden / c.vit_heads == 64 && c.vit_mlp % 64 == 0),
+            "vision tower: hidden % 64, head_dim == 64");
+  VLO_CHECK(c.vit_layers == 0 || (c.image_size % c.patch_size == 0 && (3 * c.patch_size * c.patch_size) % 64 == 0 &&
+                                  c.patch_size % 8 == 0),
+            "vision tower: patch geometry");
+  vlo_engine* e = new vlo_engine();
+  e->cfg = c;
+  e->device = device;
+  e->qkv_width = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim;
+  e->grid = c.vit_layers ? c.image_size / c.patch_size : 0;
+  e->n_patches = e->grid * e->grid;
+  e->patch_k = 3 * c.patch_size * c.patch_size;
+  e->n_frame_tokens = (c.frame_token_cls ? 1 : 0) + c.pool_h * c.pool_w;
+  e->kv_len.assign(c.max_streams, 0);
+  e->stream_open.assign(c.max_streams, 0);
+  *out = e;
+
+  const int T = c.max_step_tokens;
+  const int H = c.hidden_size;
+  // KV cache, zero-initialised once: attention may touch (masked) rows past kv_len, they must be finite.
+  const size_t kv_elems = static_cast<size_t>(c.num_layers) * 2 * kv_rows_per_layer(c) * c.head_dim;
+  if (dev_alloc_t(e, &e->kv, kv_elems, true)) return -1;
+  if (dev_alloc_t(e, &e->h, static_cast<size_t>(T) * H)) return -1;
+  if (dev_alloc_t(e, &e->xn, static_cast<size_t>(T) * H)) return -1;
+  if (dev_alloc_t(e, &e->xn_last, static_cast<size_t>(c.max_streams) * H)) return -1;
+  if (dev_alloc_t(e, &e->q, static_cast<size_t>(T) * c.num_heads * c.head_dim)) return -1;
+  if (dev_alloc_t(e, &e->attn_out, static_cast<size_t>(T) * c.num_heads * c.head_dim)) return -1;
+  if (dev_alloc_t(e, &e->act, static_cast<size_t>(T) * c.intermediate_size)) return -1;
+  if (dev_alloc_t(e, &e->logits, static_cast<size_t>(c.max_streams) * c.vocab_size)) return -1;
+  if (dev_alloc_t(e, &e->decisions, static_cast<size_t>(c.max_streams))) return -1;
+  const int widest = std::max(std::max(e->qkv_width, 2 * c.intermediate_size), H);
+  e->part_elems = static_cast<size_t>(16) * T * widest;
+  if (dev_alloc_t(e, &e->part, e->part_elems)) return -1;
+  const size_t aws = attn_ws_bytes(T, c.max_streams, c.num_heads, c.num_kv_heads);
+  if (dev_alloc(e, reinterpret_cast<void**>(&e->attn_ws), aws, false)) return -1;
+  e->meta_bytes = align256(sizeof(int) * T) * 3 + align256(sizeof(long long) * T);
+  if (dev_alloc(e, reinterpret_cast<void**>(&e->meta_dev), e->meta_bytes, false)) return -1;
+  e->stage_slot_bytes = align256(e->meta_bytes + attn_stage_bytes(T, c.max_streams, c.num_heads, c.num_kv_heads));
+  VLO_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->stage), e->stage_slot_bytes * kStageSlots));
+  for (int i = 0; i < kStageSlots; ++i) VLO_CUDA(cudaEventCreateWithFlags(&e->stage_events[i], cudaEventDisableTiming));
+
+  if (c.vit_layers > 0) {
+    const size_t rows = static_cast<size_t>(c.max_vit_batch) * e->n_patches;
+    const int C = c.vit_hidden, B = c.max_vit_batch;
+    if (dev_alloc_t(e, &e->patches, rows * e->patch_k)) return -1;
+    if (dev_alloc_t(e, &e->v_h, rows * C)) return -1;
+    if (dev_alloc_t(e, &e->v_ln32, rows * C)) return -1;
+    if (dev_alloc_t(e, &e->v_xn, rows * C)) return -1;
+    if (dev_alloc_t(e, &e->v_qkv, rows * 3 * C)) return -1;
+    if (dev_alloc_t(e, &e->v_attn, rows * C)) return -1;
+    if (dev_alloc_t(e, &e->v_mlp, rows * c.vit_mlp)) return -1;
+    if (dev_alloc_t(e, &e->v_pa, static_cast<size_t>(B) * C)) return -1;
+    if (dev_alloc_t(e, &e->v_resid, static_cast<size_t>(B) * C)) return -1;
+    if (dev_alloc_t(e, &e->v_lnh, static_cast<size_t>(B) * C)) return -1;
+    if (dev_alloc_t(e, &e->v_m1, static_cast<size_t>(B) * c.vit_mlp)) return -1;
+    if (dev_alloc_t(e, &e->v_m2, static_cast<size_t>(B) * C)) return -1;
+  }
+  {
+    const size_t trows = static_cast<size_t>(std::max(1, c.max_vit_batch)) * std::max(1, e->n_frame_tokens);
+    const int C = std::max(64, c.vit_hidden);
+    if (dev_alloc_t(e, &e->tokens32, trows * C)) return -1;
+    if (dev_alloc_t(e, &e->tokens16, trows * C)) return -1;
+    if (dev_alloc_t(e, &e->conn_mid, trows * H)) return -1;
+  }
+  return 0;
+}
+
+int vlo_engine_destroy(vlo_engine* e) {
+  if (e == nullptr) return 0;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->stage) cudaFreeHost(e->stage);
+  for (int i = 0; i < kStageSlots; ++i)
+    if (e->stage_events[i]) cudaEventDestroy(e->stage_events[i]);
+  delete e;
+  return 0;
+}
+
+int64_t vlo_engine_device_bytes(vlo_engine* e) { return e ? e->device_bytes : 0; }
+
+int vlo_load_tensor(vlo_engine* e, const char* name, const void* d_ptr, int64_t n_bytes) {
+  VLO_CHECK(e != nullptr && name != nullptr && d_ptr != nullptr && n_bytes > 0, "bad argument");
+  VLO_CHECK((reinterpret_cast<uintptr_t>(d_ptr) & 15) == 0, std::string("tensor '") + name + "' is not 16-byte aligned");
+  e->tensors[name] = {d_ptr, n_bytes};
+  e->finalized = false;
+  return 0;
+}
+
+int vlo_finalize_weights(vlo_engine* e) {
+  VLO_CHECK(e != nullptr, "null engine");
+  const vlo_config& c = e->cfg;
+  const int64_t H = c.hidden_size, I = c.intermediate_size, V = c.vocab_size;
+  e->has_decoder = e->tensors.count("embed") > 0;
+  if (e->has_decoder) {
+    if (lookup(e, "embed", V * H, &e->embed)) return -1;
+    if (lookup(e, "final_norm", H, &e->final_norm)) return -1;
+    if (lookup(e, "lm_head", V * H, &e->lm_head)) return -1;
+    auto it = e->tensors.find("rope.cos");
+    if (it == e->tensors.end()) return fail("missing weight tensor 'rope.cos'");
+    e->rope_positions = it->second.second / (64 * 2);
+    VLO_CHECK(e->rope_positions >= c.max_kv_tokens, "rope tables shorter than max_kv_tokens");
+    if (lookup(e, "rope.cos", e->rope_positions * 64, &e->rope_cos)) return -1;
+    if (lookup(e, "rope.sin", e->rope_positions * 64, &e->rope_sin)) return -1;
+    e->dec.resize(c.num_layers);
+    for (int l = 0; l < c.num_layers; ++l) {
+      const std::string p = "L" + std::to_string(l) + ".";
+      DecLayer& d = e->dec[l];
+      if (lookup(e, p + "in_norm", H, &d.in_norm)) return -1;
+      if (lookup(e, p + "qkv", static_cast<int64_t>(e->qkv_width) * H, &d.qkv)) return -1;
+      if (lookup(e, p + "o", H * c.num_heads * c.head_dim, &d.o)) return -1;
+      if (lookup(e, p + "post_norm", H, &d.post_norm)) return -1;
+      if (lookup(e, p + "gate_up", 2 * I * H, &d.gate_up)) return -1;
+      if (lookup(e, p + "down", H * I, &d.down)) return -1;
+    }
+  }
+  e->has_connector = e->tensors.count("conn.0.w") > 0;
+  if (e->has_connector) {
+    const int64_t C = c.vit_hidden;
+    if (lookup(e, "conn.0.w", H * C, &e->conn0_w)) return -1;
+    if (lookup(e, "conn.0.b", H, &e->conn0_b)) return -1;
+    if (lookup(e, "conn.2.w", H * H, &e->conn2_w)) return -1;
+    if (lookup(e, "conn.2.b", H, &e->conn2_b)) return -1;
+  }
+  e->has_vit = c.vit_layers > 0 && e->tensors.count("vit.patch.w") > 0;
+  if (e->has_vit) {
+    const int64_t C = c.vit_hidden, M = c.vit_mlp;
+    if (lookup(e, "vit.patch.w", C * e->patch_k, &e->patch_w)) return -1;
+    if (lookup(e, "vit.patch.b", C, &e->patch_b)) return -1;
+    if (lookup(e, "vit.pos", static_cast<int64_t>(e->n_patches) * C, &e->pos_emb)) return -1;
+    if (lookup(e, "vit.post_ln.w", C, &e->post_ln_w)) return -1;
+    if (lookup(e, "vit.post_ln.b", C, &e->post_ln_b)) return -1;
+    e->vit.resize(c.vit_layers);
+    for (int l = 0; l < c.vit_layers; ++l) {
+      const std::string p = "vit.L" + std::to_string(l) + ".";
+      VitLayer& v = e->vit[l];
+      if (lookup(e, p + "ln1.w", C, &v.ln1_w) || lookup(e, p + "ln1.b", C, &v.ln1_b)) return -1;
+      if (lookup(e, p + "ln2.w", C, &v.ln2_w) || lookup(e, p + "ln2.b", C, &v.ln2_b)) return -1;
+      if (lookup(e, p + "qkv.w", 3 * C * C, &v.qkv_w) || lookup(e, p + "qkv.b", 3 * C, &v.qkv_b)) return -1;
+      if (lookup(e, p + "out.w", C * C, &v.out_w) || lookup(e, p + "out.b", C, &v.out_b)) return -1;
+      if (lookup(e, p + "fc1.w", M * C, &v.fc1_w) || lookup(e, p + "fc1.b", M, &v.fc1_b)) return -1;
+      if (lookup(e, p + "fc2.w", C * M, &v.fc2_w) || lookup(e, p + "fc2.b", C, &v.fc2_b)) return -1;
+    }
+    if (c.frame_token_cls) {
+      if (lookup(e, "vit.head.q", C, &e->head_q)) return -1;
+      if (lookup(e, "vit.head.kv.w", 2 * C * C, &e->head_kv_w) || lookup(e, "vit.head.kv.b", 2 * C, &e->head_kv_b)) return -1;
+      if (lookup(e, "vit.head.out.w", C * C, &e->head_out_w) || lookup(e, "vit.head.out.b", C, &e->head_out_b)) return -1;
+      if (lookup(e, "vit.head.ln.w", C, &e->head_ln_w) || lookup(e, "vit.head.ln.b", C, &e->head_ln_b)) return -1;
+      if (lookup(e, "vit.head.fc1.w", M * C, &e->head_fc1_w) || lookup(e, "vit.head.fc1.b", M, &e->head_fc1_b)) return -1;
+      if (lookup(e, "vit.head.fc2.w", C * M, &e->head_fc2_w) || lookup(e, "vit.head.fc2.b", C, &e->head_fc2_b)) return -1;
+    }
+  }
+  e->finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ streams
+int vlo_stream_open(vlo_engine* e, int* stream_id) {
+  VLO_CHECK(e != nullptr && stream_id != nullptr, "null argument");
+  for (int i = 0; i < e->cfg.max_streams; ++i)
+    if (!e->stream_open[i]) {
+      e->stream_open[i] = 1;
+      e->kv_len[i] = 0;
+      *stream_id = i;
+      return 0;
+    }
+  return fail("no free stream slot (max_streams = " + std::to_string(e->cfg.max_streams) + ")");
+}
+int vlo_stream_reset(vlo_engine* e, int sid) {
+  if (check_stream(e, sid)) return -1;
+  e->kv_len[sid] = 0;
+  return 0;
+}
+int vlo_stream_close(vlo_engine* e, int sid) {
+  if (check_stream(e, sid)) return -1;
+  e->stream_open[sid] = 0;
+  e->kv_len[sid] = 0;
+  return 0;
+}
+int vlo_kv_len(vlo_engine* e, int sid, int* out_len) {
+  if (check_stream(e, sid)) return -1;
+  *out_len = e->kv_len[sid];
+  return 0;
+}
+int vlo_kv_truncate(vlo_engine* e, int sid, int new_len) {
+  if (check_stream(e, sid)) return -1;
+  VLO_CHECK(new_len >= 0 && new_len <= e->kv_len[sid], "kv_truncate: new_len must be within [0, kv_len]");
+  e->kv_len[sid] = new_len;
+  return 0;
+}
+int vlo_kv_fill_synthetic(vlo_engine* e, int sid, int n_tokens, uint64_t seed, void* cuda_stream) {
+  if (check_stream(e, sid)) return -1;
+  const vlo_config& c = e->cfg;
+  VLO_CHECK(n_tokens >= 0 && n_tokens <= c.max_kv_tokens, "kv_fill: n_tokens out of range");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  for (int l = 0; l < c.num_layers; ++l)
+    for (int v = 0; v < 2; ++v)
+      for (int hd = 0; hd < c.num_kv_heads; ++hd) {
+        const long long row0 = (static_cast<long long>(sid) * c.num_kv_heads + hd) * c.max_kv_tokens;
+        if (n_tokens > 0) {
+          kv_fill_kernel<<<std::min(1024, (n_tokens * 128 + 255) / 256), 256, 0, st>>>(
+              kv_layer_base(e, l, v), row0, n_tokens, seed + (static_cast<uint64_t>(l) * 2 + v) * 1315423911ull + hd * 2654435761ull);
+        }
+      }
+  VLO_LAUNCH_CHECK();
+  e->kv_len[sid] = n_tokens;
+  return 0;
+}
+int vlo_kv_read(vlo_engine* e, int sid, int layer, int is_v, void* d_out, void* cuda_stream) {
+  if (check_stream(e, sid)) return -1;
+  const vlo_config& c = e->cfg;
+  VLO_CHECK(layer >= 0 && layer < c.num_layers, "layer out of range");
+  const int len = e->kv_len[sid];
+  if (len == 0) return 0;
+  const bf16* src = kv_layer_base(e, layer, is_v) + static_cast<size_t>(sid) * c.num_kv_heads * c.max_kv_tokens * c.head_dim;
+  VLO_CUDA(cudaMemcpy2DAsync(d_out, static_cast<size_t>(len) * c.head_dim * 2, src,
+                             static_cast<size_t>(c.max_kv_tokens) * c.head_dim * 2, static_cast<size_t>(len) * c.head_dim * 2,
+                             c.num_kv_heads, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(cuda_stream)));
+  return 0;
+}
+int vlo_kv_write(vlo_engine* e, int sid, int layer, int is_v, const void* d_in, int n_tokens, void* cuda_stream) {
+  if (check_stream(e, sid)) return -1;
+  const vlo_config& c = e->cfg;
+  VLO_CHECK(layer >= 0 && layer < c.num_layers, "layer out of range");
+  VLO_CHECK(n_tokens > 0 && n_tokens <= c.max_kv_tokens, "kv_write: n_tokens out of range");
+  bf16* dst = kv_layer_base(e, layer, is_v) + static_cast<size_t>(sid) * c.num_kv_heads * c.max_kv_tokens * c.head_dim;
+  VLO_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(c.max_kv_tokens) * c.head_dim * 2, d_in,
+                             static_cast<size_t>(n_tokens) * c.head_dim * 2, static_cast<size_t>(n_tokens) * c.head_dim * 2,
+                             c.num_kv_heads, cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(cuda_stream)));
+  e->kv_len[sid] = n_tokens;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ vision
+int vlo_connector(vlo_engine* e, const void* d_tokens, int n_rows, void* d_out, void* cuda_stream) {
+  VLO_CHECK(e != nullptr && e->finalized && e->has_connector, "connector weights not loaded");
+  const vlo_config& c = e->cfg;
+  const int cap = std::max(1, c.max_vit_batch) * std::max(1, e->n_frame_tokens);
+  VLO_CHECK(n_rows > 0 && n_rows <= cap, "connector: n_rows exceeds max_vit_batch * frame_num_tokens");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  // Linear -> GELU (python erf form, bf16) -> Linear   (models/live_llama/modeling_live_llama.py:18-22)
+  if (gemm_store16(FMT_BF16, 1, e->conn0_w, c.hidden_size, d_tokens, n_rows, c.vit_hidden, e->conn_mid, c.hidden_size,
+                   e->conn0_b, ACT_GELU_ERF_PY, swap_bn(n_rows), st))
+    return -1;
+  return gemm_store16(FMT_BF16, 1, e->conn2_w, c.hidden_size, e->conn_mid, n_rows, c.hidden_size, d_out, c.hidden_size,
+                      e->conn2_b, ACT_NONE, swap_bn(n_rows), st);
+}
+
+int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, float* d_vit_tokens, void* cuda_stream) {
+  VLO_CHECK(e != nullptr && e->finalized && e->has_vit, "vision tower weights not loaded");
+  const vlo_config& c = e->cfg;
+  VLO_CHECK(B > 0 && B <= c.max_vit_batch, "vit_encode: batch exceeds max_vit_batch");
+  VLO_CHECK(e->n_frame_tokens > 0, "no frame tokens configured");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int C = c.vit_hidden, M = c.vit_mlp, P = e->n_patches, rows = B * P;
+  const size_t ln_smem = static_cast<size_t>(C) * sizeof(float);
+
+  // K1/K2: normalise + patchify, then patch-embed GEMM with bias + position embedding epilogue
+  {
+    const long long total = static_cast<long long>(rows) * e->patch_k / 8;
+    patchify_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 4096)), 256, 0, st>>>(
+        d_frames, e->patches, B, c.image_size, c.patch_size);
+    VLO_LAUNCH_CHECK();
+    count_launch();
+    GemmCall g{};
+    g.fmt = FMT_F16;
+    g.swap = 0;
+    g.epi = EPI_PATCH32;
+    g.a = e->patches;
+    g.rows_a = rows;
+    g.b = e->patch_w;
+    g.rows_b = C;
+    g.k = e->patch_k;
+    g.out = e->v_h;
+    g.ld_out = C;
+    g.bias = e->patch_b;
+    g.pos = e->pos_emb;
+    g.pos_rows = P;
+    g.splits = 1;
+    g.bn = vit_bn(rows, C);
+    if (gemm_launch(g, st)) return -1;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLO_CUDA(cudaFuncSetAttribute(vit_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kVitSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap tm_qkv;
+  if (tmap_2d_sw128(e->v_qkv, rows, 3 * C, kVitBlk, FMT_F16, &tm_qkv)) return -1;
+  const float scale_log2 = 1.4426950408889634f / 8.0f;  // head_dim 64
+  auto resid_gemm = [&](const __half* a, const __half* w, const float* bias, int k) -> int {
+    GemmCall g{};
+    g.fmt = FMT_F16;
+    g.swap = 0;
+    g.epi = EPI_RESID32;
+    g.a = a;
+    g.rows_a = rows;
+    g.b = w;
+    g.rows_b = C;
+    g.k = k;
+    g.out = e->v_h;
+    g.ld_out = C;
+    g.bias = bias;
+    g.splits = 1;
+    g.bn = vit_bn(rows, C);
+    return gemm_launch(g, st);
+  };
+  for (int l = 0; l < c.vit_layers; ++l) {
+    const VitLayer& v = e->vit[l];
+    layernorm_kernel<float><<<rows, 256, ln_smem, st>>>(e->v_h, v.ln1_w, v.ln1_b, e->v_xn, nullptr, C, c.vit_ln_eps);
+    VLO_LAUNCH_CHECK();
+    if (gemm_store16(FMT_F16, 0, e->v_xn, rows, v.qkv_w, 3 * C, C, e->v_qkv, 3 * C, v.qkv_b, ACT_NONE, vit_bn(rows, 3 * C), st))
+      return -1;
+    vit_attn_kernel<<<dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), kVitThreads, kVitSmemBytes, st>>>(
+        tm_qkv, e->v_attn, P, C, scale_log2);
+    VLO_LAUNCH_CHECK();
+    if (resid_gemm(e->v_attn, v.out_w, v.out_b, C)) return -1;
+    layernorm_kernel<float><<<rows, 256, ln_smem, st>>>(e->v_h, v.ln2_w, v.ln2_b, e->v_xn, nullptr, C, c.vit_ln_eps);
+    VLO_LAUNCH_CHECK();
+    if (gemm_store16(FMT_F16, 0, e->v_xn, rows, v.fc1_w, M, C, e->v_mlp, M, v.fc1_b, ACT_GELU_TANH, vit_bn(rows, M), st))
+      return -1;
+    if (resid_gemm(e->v_mlp, v.fc2_w, v.fc2_b, M)) return -1;
+    count_launch(3);
+  }
+  // post-LN: fp16 copy feeds the MAP head, fp32 copy feeds the pool
+  layernorm_kernel<float><<<rows, 256, ln_smem, st>>>(e->v_h, e->post_ln_w, e->post_ln_b, e->v_xn, e->v_ln32, C, c.vit_ln_eps);
+  VLO_LAUNCH_CHECK();
+  count_launch();
+  const int NT = e->n_frame_tokens;
+  const int cls = c.frame_token_cls ? 1 : 0;
+  if (c.pool_h * c.pool_w > 0) {
+    const long long total = static_cast<long long>(B) * c.pool_h * c.pool_w * C;
+    pool_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 2048)), 256, 0, st>>>(
+        e->v_ln32, e->tokens32, B, e->grid, C, c.pool_h, c.pool_w, NT, cls);
+    VLO_LAUNCH_CHECK();
+    count_launch();
+  }
+  if (cls) {
+    // MAP head: K/V projection of all tokens, 1-query attention, out-proj, LN, MLP, residual
+    if (gemm_store16(FMT_F16, 0, e->v_xn, rows, e->head_kv_w, 2 * C, C, e->v_qkv, 2 * C, e->head_kv_b, ACT_NONE,
+                     vit_bn(rows, 2 * C), st))
+      return -1;
+    probe_attn_kernel<<<dim3(c.vit_heads, B), 128, static_cast<size_t>(P) * sizeof(float), st>>>(e->v_qkv, e->head_q, e->v_pa, P, C, 0.125f);
+    VLO_LAUNCH_CHECK();
+    if (gemm_store16(FMT_F16, 1, e->head_out_w, C, e->v_pa, B, C, e->v_resid, C, e->head_out_b, ACT_NONE, swap_bn(B), st)) return -1;
+    layernorm_kernel<__half><<<B, 256, ln_smem, st>>>(e->v_resid, e->head_ln_w, e->head_ln_b, e->v_lnh, nullptr, C, c.vit_ln_eps);
+    VLO_LAUNCH_CHECK();
+    if (gemm_store16(FMT_F16, 1, e->head_fc1_w, M, e->v_lnh, B, C, e->v_m1, M, e->head_fc1_b, ACT_GELU_TANH, swap_bn(B), st)) return -1;
+    if (gemm_store16(FMT_F16, 1, e->head_fc2_w, C, e->v_m1, B, M, e->v_m2, C, e->head_fc2_b, ACT_NONE, swap_bn(B), st)) return -1;
+    cls_residual_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(e->v_resid, e->v_m2, e->tokens32, B, C, NT);
+    VLO_LAUNCH_CHECK();
+    count_launch(3);
+  }
+  const long long ntok_elems = static_cast<long long>(B) * NT * C;
+  if (d_vit_tokens)
+    VLO_CUDA(cudaMemcpyAsync(d_vit_tokens, e->tokens32, ntok_elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (d_out) {
+    f32_to_bf16_kernel<<<static_cast<int>(std::min<long long>((ntok_elems + 255) / 256, 2048)), 256, 0, st>>>(e->tokens32, e->tokens16, ntok_elems);
+    VLO_LAUNCH_CHECK();
+    count_launch();
+    return vlo_connector(e, e->tokens16, B * NT, d_out, cuda_stream);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ decoder
+int vlo_embed_tokens(vlo_engine* e, const int64_t* d_ids, int n, void* d_out, void* cuda_stream) {
+  VLO_CHECK(e != nullptr && e->finalized && e->has_decoder, "decoder weights not loaded");
+  VLO_CHECK(n > 0, "embed_tokens: n must be positive");
+  embed_rows_kernel<<<n, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      reinterpret_cast<const long long*>(d_ids), nullptr, n, e->embed, e->cfg.vocab_size, e->cfg.hidden_size,
+      static_cast<bf16*>(d_out));
+  VLO_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+}
+
+int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const int32_t* h_q_lens,
+                 const int64_t* d_prefix_ids, const void* d_embeds, void* d_last_logits, vlo_decision* d_decisions,
+                 int interval_id, void* cuda_stream) {
+  VLO_CHECK(e != nullptr && e->finalized && e->has_decoder, "decoder weights not loaded");
+  const vlo_config& c = e->cfg;
+  VLO_CHECK(n_seqs > 0 && n_seqs <= c.max_streams, "step: n_seqs out of range");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int H = c.hidden_size;
+  int T = 0;
+  for (int i = 0; i < n_seqs; ++i) {
+    if (check_stream(e, h_stream_ids[i])) return -1;
+    for (int j = 0; j < i; ++j) VLO_CHECK(h_stream_ids[j] != h_stream_ids[i], "step: a stream appears twice in one batch");
+    VLO_CHECK(h_q_lens[i] > 0, "step: q_len must be positive");
+    VLO_CHECK(e->kv_len[h_stream_ids[i]] + h_q_lens[i] <= c.max_kv_tokens,
+              "step: KV cache capacity exceeded for stream " + std::to_string(h_stream_ids[i]));
+    T += h_q_lens[i];
+  }
+  VLO_CHECK(T <= c.max_step_tokens, "step: total new tokens exceed max_step_tokens");
+
+  // ---- per-step metadata: built on the host, one pinned slot, uploaded once, reused by all layers
+  uint8_t* hs;
+  int slot;
+  if (stage_acquire(e, &hs, &slot)) return -1;
+  const size_t o_pos = 0, o_last = align256(sizeof(int) * c.max_step_tokens), o_first = 2 * o_last,
+               o_row = 3 * o_last;
+  int* tok_pos = reinterpret_cast<int*>(hs + o_pos);
+  int* last_index = reinterpret_cast<int*>(hs + o_last);
+  int* first_rows = reinterpret_cast<int*>(hs + o_first);
+  long long* tok_kvrow = reinterpret_cast<long long*>(hs + o_row);
+  std::vector<AttnSeq> seqs(n_seqs);
+  int t = 0;
+  for (int i = 0; i < n_seqs; ++i) {
+    const int sid = h_stream_ids[i], ql = h_q_lens[i], past = e->kv_len[sid];
+    const long long row0 = static_cast<long long>(sid) * c.num_kv_heads * c.max_kv_tokens;
+    first_rows[i] = t;
+    for (int j = 0; j < ql; ++j) {
+      tok_pos[t + j] = past + j;
+      tok_kvrow[t + j] = row0;
+      last_index[t + j] = (j == ql - 1) ? i : -1;
+    }
+    seqs[i] = AttnSeq{t, ql, past + ql, row0, c.max_kv_tokens};
+    t += ql;
+  }
+  VLO_CUDA(cudaMemcpyAsync(e->meta_dev, hs, e->meta_bytes, cudaMemcpyHostToDevice, st));
+  const int* d_tok_pos = reinterpret_cast<const int*>(e->meta_dev + o_pos);
+  const int* d_last_index = reinterpret_cast<const int*>(e->meta_dev + o_last);
+  const int* d_first_rows = reinterpret_cast<const int*>(e->meta_dev + o_first);
+  const long long* d_tok_kvrow = reinterpret_cast<const long long*>(e->meta_dev + o_row);
+  AttnPlan plan{};
+  if (attn_plan(&plan, e->attn_ws, hs + e->meta_bytes, seqs.data(), n_seqs, T, c.num_heads, c.num_kv_heads, c.head_dim, st))
+    return -1;
+  if (stage_release(e, slot, st)) return -1;
+
+  // ---- residual stream <- packed input embeddings (+ prefix-token rows gathered by id)
+  VLO_CUDA(cudaMemcpyAsync(e->h, d_embeds, static_cast<size_t>(T) * H * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+  if (d_prefix_ids != nullptr) {
+    embed_rows_kernel<<<n_seqs, 256, 0, st>>>(reinterpret_cast<const long long*>(d_prefix_ids), d_first_rows, n_seqs,
+                                              e->embed, c.vocab_size, H, e->h);
+    VLO_LAUNCH_CHECK();
+    count_launch();
+  }
+
+  const size_t norm_smem = static_cast<size_t>(H) * sizeof(float);
+  auto resid_norm = [&](int n_splits, long long split_stride, const bf16* w, bool last) -> int {
+    ResidNormParams p{};
+    p.part = e->part;
+    p.n_splits = n_splits;
+    p.split_stride = split_stride;
+    p.h = e->h;
+    p.w = w;
+    p.xn = e->xn;
+    p.xn_last = last ? e->xn_last : nullptr;
+    p.last_index = last ? d_last_index : nullptr;
+    p.H = H;
+    p.eps = c.rms_norm_eps;
+    resid_rmsnorm_kernel<<<T, 256, norm_smem, st>>>(p);
+    VLO_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+  };
+
+  if (resid_norm(0, 0, e->dec[0].in_norm, false)) return -1;
+  const int attn_width = c.num_heads * c.head_dim;
+  for (int l = 0; l < c.num_layers; ++l) {
+    const DecLayer& d = e->dec[l];
+    int S = 1;
+    // fused q|k|v projection -> partials; fix-up + RoPE + in-place KV append
+    if (gemm_partial(e, d.qkv, e->qkv_width, e->xn, T, H, &S, st)) return -1;
+    {
+      QkvRopeParams p{};
+      p.part = e->part;
+      p.n_splits = S;
+      p.split_stride = static_cast<long long>(T) * e->qkv_width;
+      p.cos_tab = e->rope_cos;
+      p.sin_tab = e->rope_sin;
+      p.tok_pos = d_tok_pos;
+      p.tok_kvrow = d_tok_kvrow;
+      p.kv_head_stride = c.max_kv_tokens;
+      p.q_out = e->q;
+      p.k_cache = kv_layer_base(e, l, 0);
+      p.v_cache = kv_layer_base(e, l, 1);
+      p.n_heads = c.num_heads;
+      p.n_kv_heads = c.num_kv_heads;
+      qkv_rope_append_kernel<<<dim3(T, c.num_heads + 2 * c.num_kv_heads), 64, 0, st>>>(p);
+      VLO_LAUNCH_CHECK();
+      count_launch();
+    }
+    if (attn_run(plan, e->q, kv_layer_base(e, l, 0), kv_layer_base(e, l, 1), kv_rows_per_layer(c), e->attn_out,
+                 c.num_heads, c.num_kv_heads, c.head_dim, st))
+      return -1;
+    if (gemm_partial(e, d.o, H, e->attn_out, T, attn_width, &S, st)) return -1;
+    if (resid_norm(S, static_cast<long long>(T) * H, d.post_norm, false)) return -1;
+    if (gemm_partial(e, d.gate_up, 2 * c.intermediate_size, e->xn, T, H, &S, st)) return -1;
+    {
+      SwigluParams p{};
+      p.part = e->part;
+      p.n_splits = S;
+      p.split_stride = static_cast<long long>(T) * 2 * c.intermediate_size;
+      p.act = e->act;
+      p.T = T;
+      p.I = c.intermediate_size;
+      const long long n2 = static_cast<long long>(T) * c.intermediate_size / 2;
+      swiglu_kernel<<<static_cast<int>(std::min<long long>((n2 + 255) / 256, 4 * kNumSMs)), 256, 0, st>>>(p);
+      VLO_LAUNCH_CHECK();
+      count_launch();
+    }
+    if (gemm_partial(e, d.down, H, e->act, T, c.intermediate_size, &S, st)) return -1;
+    const bool is_last = (l == c.num_layers - 1);
+    if (resid_norm(S, static_cast<long long>(T) * H, is_last ? e->final_norm : e->dec[l + 1].in_norm, is_last)) return -1;
+  }
+  // ---- last-position lm_head + on-device decision
+  bf16* logits = d_last_logits ? static_cast<bf16*>(d_last_logits) : e->logits;
+  if (gemm_store16(FMT_BF16, 1, e->lm_head, c.vocab_size, e->xn_last, n_seqs, H, logits, c.vocab_size, nullptr, ACT_NONE,
+                   swap_bn(n_seqs), st))
+    return -1;
+  DecisionOut* dec_out = d_decisions ? reinterpret_cast<DecisionOut*>(d_decisions) : e->decisions;
+  decision_kernel<<<n_seqs, 1024, 0, st>>>(logits, c.vocab_size, interval_id, dec_out);
+  VLO_LAUNCH_CHECK();
+  count_launch();
+
+  for (int i = 0; i < n_seqs; ++i) e->kv_len[h_stream_ids[i]] += h_q_lens[i];
+  e->last_step_tokens = T;
+  return 0;
+}
+
+int vlo_step(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const int32_t* h_q_lens, const void* d_embeds,
+             void* d_last_logits, vlo_decision* d_decisions, int interval_id, void* cuda_stream) {
+  return vlo_step_ids(e, n_seqs, h_stream_ids, h_q_lens, nullptr, d_embeds, d_last_logits, d_decisions, interval_id,
+                      cuda_stream);
+}
+
+int vlo_last_step_hidden(vlo_engine* e, void* d_hidden, void* cuda_stream) {
+  VLO_CHECK(e != nullptr && e->last_step_tokens > 0, "no decoder step has run");
+  VLO_CUDA(cudaMemcpyAsync(d_hidden, e->xn, static_cast<size_t>(e->last_step_tokens) * e->cfg.hidden_size * sizeof(bf16),
+                           cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(cuda_stream)));
+  return 0;
+}
+
+int vlo_last_step_logits(vlo_engine* e, void* d_logits, void* cuda_stream) {
+  VLO_CHECK(e != nullptr && e->last_step_tokens > 0, "no decoder step has run");
+  const vlo_config& c = e->cfg;
+  return gemm_store16(FMT_BF16, 1, e->lm_head, c.vocab_size, e->xn, e->last_step_tokens, c.hidden_size, d_logits,
+                      c.vocab_size, nullptr, ACT_NONE, swap_bn(e->last_step_tokens), static_cast<cudaStream_t>(cuda_stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+"""Streaming session state machine — the engine-backed `LiveInfer`.
+
+Same public surface and protocol as the reference's demo/inference.py:12-124 (`load_video`,
+`input_video_stream`, `input_query_stream`, `__call__`, `reset`, `frame_token_interval_threshold`) so
+demo/cli.py and demo/app.py can drive it unchanged.  Differences, all behind the same results:
+  * the device is a parameter, not a hard-coded 'cuda';
+  * the speak/silent decision and the greedy argmax are computed on the device; one 32-byte read-back
+    per frame / generated token replaces the reference's two tensor-`if` syncs (demo/inference.py:77,80);
+  * the steady-state frame step feeds [interval-token id | 10 frame embeddings] and lets the engine gather
+    the token row, so no separate embedding launch or torch.cat is needed.
+"""
+from __future__ import annotations
+
+import collections
+import logging
+from dataclasses import asdict
+
+import torch
+
+from .config import LiveArguments, parse_args
+from .modeling_live import LiveLlamaForCausalLM, StreamKV, build_model_and_tokenizer, fast_greedy_generate
+
+logger = logging.getLogger("liveinfer")
+
+
+class LiveInfer:
+    def __init__(self, args: LiveArguments = None, *, model: LiveLlamaForCausalLM = None, tokenizer=None,
+                 device: str = None, stream: StreamKV = None) -> None:
+        args = args or parse_args()
+        if model is None:
+            kw = asdict(args)
+            kw["device"] = device or args.device
+            model, tokenizer = build_model_and_tokenizer(is_training=False, set_vision_inside=True, **kw)
+        self.model, self.tokenizer = model, tokenizer
+        self.device = model.device
+        cfg = model.config
+        # visual
+        self.hidden_size = cfg.hidden_size
+        self.frame_fps = args.frame_fps
+        self.frame_interval = 1 / self.frame_fps
+        self.frame_resolution = cfg.frame_resolution
+        self.frame_num_tokens = cfg.frame_num_tokens
+        self.frame_v_placeholder = cfg.v_placeholder * self.frame_num_tokens
+        self.frame_token_interval_id = cfg.frame_token_interval_id
+        self.frame_placeholder_ids = torch.tensor(cfg.v_placeholder_id).repeat(cfg.frame_num_tokens).reshape(1, -1)
+        # generation
+        self.system_prompt = args.system_prompt
+        self.inplace_output_ids = torch.zeros(1, 100, dtype=torch.long)  # host buffer: ids are decided on device, read back per token
+        self.frame_token_interval_threshold = 0.725
+        self.eos_token_id = cfg.eos_token_id
+        self.stream_end_id = cfg.stream_end_id
+        tok = self.tokenizer
+        self._start_ids = tok.apply_chat_template([{'role': 'system', 'content': self.system_prompt}], add_stream_prompt=True, return_tensors='pt')
+        self._added_stream_prompt_ids = tok.apply_chat_template([{}], add_stream_prompt=True, return_tensors='pt')
+        self._added_stream_generation_ids = tok.apply_chat_template([{}], add_stream_generation_prompt=True, return_tensors='pt')
+        self._kv = stream if stream is not None else model.new_stream()
+        # test seam: decision_hook(decision, call_index) -> decision lets a test script the model's choices
+        # (random weights never emit the "]\\n" / EOS protocol ids); None in production.
+        self.decision_hook = None
+        self._n_calls = 0
+        self.reset()
+
+    # ------------------------------------------------------------------ session control
+    def reset(self):
+        self.query_queue = collections.deque()
+        self.frame_embeds_queue = collections.deque()
+        self.video_time = 0
+        self.last_frame_idx = -1
+        self.video_tensor = None
+        self.last_ids = torch.tensor([[]], dtype=torch.long)
+        self._kv.engine.stream_reset(self._kv.stream_id)
+        self.past_key_values = None
+
+    def load_video(self, video_path_or_tensor):
+        """Reference: read_video(...)[0].to('cuda') (demo/inference.py:111-115).  Accepts a uint8
+        [T,3,H,W] tensor directly (synthetic clips) or a path decodable by torchvision/cv2."""
+        if isinstance(video_path_or_tensor, torch.Tensor):
+            vt = video_path_or_tensor
+        else:
+            vt = _read_video_tchw(video_path_or_tensor)
+        self.video_tensor = vt.to(self.device)
+        self.num_video_frames = self.video_tensor.size(0)
+        self.video_duration = self.video_tensor.size(0) / self.frame_fps
+        logger.warning(f'{"tensor" if isinstance(video_path_or_tensor, torch.Tensor) else video_path_or_tensor} -> '
+                       f'{tuple(self.video_tensor.shape)}, {self.frame_fps} FPS')
+
+    def input_query_stream(self, query, history=None, video_time=None):
+        self.query_queue.append((self.video_time if video_time is None else video_time, query))
+        if not self.past_key_values:
+            return f'(NOTE: No video stream here. Please select or upload a video. Then the assistant will answer "{query} (at {self.video_time}s)" in the video stream)'
+        return f'(NOTE: Received "{query}" (at {self.video_time}s). Please wait until previous frames have been processed)'
+
+    def input_video_stream(self, video_time):
+        frame_idx = int(video_time * self.frame_fps)
+        if frame_idx > self.last_frame_idx:
+            ranger = range(self.last_frame_idx + 1, frame_idx + 1)
+            embeds = self.model.visual_embed(self.video_tensor[ranger.start:ranger.stop]).split(self.frame_num_tokens)
+            self.frame_embeds_queue.extend([(r / self.frame_fps, e) for r, e in zip(ranger, embeds)])
+        self.last_frame_idx = frame_idx
+        self.video_time = video_time
+
+    # ------------------------------------------------------------------ decoder steps
+    def _forward(self, ids: torch.Tensor, frame_embeds: torch.Tensor = None):
+        """One KV-append step over [embed(ids) ; frame_embeds]; returns the device decision (host copy)."""
+        eng = self.model.engine
+        ids = ids.reshape(-1)
+        n_ids = ids.numel()
+        if frame_embeds is not None and n_ids == 1:
+            # steady state: the engine gathers the single prefix row by id
+            packed = torch.empty(1 + frame_embeds.shape[0], self.hidden_size, dtype=torch.bfloat16, device=self.device)
+            packed[1:] = frame_embeds
+            eng.step([self._kv.stream_id], [packed.shape[0]], packed, prefix_ids=ids.to(self.device))
+        else:
+            parts = [self.model.get_input_embeddings()(ids.to(self.device)).view(-1, self.hidden_size)] if n_ids else []
+            if frame_embeds is not None:
+                parts.append(frame_embeds.view(-1, self.hidden_size))
+            packed = torch.cat(parts, 0)
+            eng.step([self._kv.stream_id], [packed.shape[0]], packed)
+        self.past_key_values = self._kv
+        dec = eng.read_decisions(1)[0]
+        if self.decision_hook is not None:
+            dec = self.decision_hook(dec, self._n_calls)
+        self._n_calls += 1
+        return dec
+
+    def _call_for_response(self, video_time, query):
+        if query is not None:
+            self.last_ids = self.tokenizer.apply_chat_template([{'role': 'user', 'content': query}], add_stream_query_prompt=True, add_generation_prompt=True, return_tensors='pt')
+        else:
+            assert int(self.last_ids) == self.stream_end_id, f'{self.last_ids} != {self.stream_end_id}'  # "]\n" closes the frame list
+            self.last_ids = self._added_stream_generation_ids
+        ids = self.last_ids
+        n = 0
+        for i in range(self.inplace_output_ids.size(1)):  # fast_greedy_generate, models/modeling_live.py:173-182
+            new_id = self._forward(ids).argmax_id
+            self.inplace_output_ids[0, i] = new_id
+            n = i + 1
+            if new_id == self.eos_token_id:
+                break
+            ids = torch.tensor([[new_id]], dtype=torch.long)
+        output_ids = self.inplace_output_ids[:, :n]
+        self.last_ids = output_ids[:, -1:].clone()
+        if query:
+            query = f'(Video Time = {video_time}s) User: {query}'
+        response = f'(Video Time = {video_time}s) Assistant:{self.tokenizer.decode(output_ids[0], skip_special_tokens=True, clean_up_tokenization_spaces=True)}'
+        return query, response
+
+    def _call_for_streaming(self):
+        while self.frame_embeds_queue:
+            # 1. a query that is due before the next frame is answered first
+            if self.query_queue and self.frame_embeds_queue[0][0] > self.query_queue[0][0]:
+                video_time, query = self.query_queue.popleft()
+                return video_time, query
+            video_time, frame_embeds = self.frame_embeds_queue.popleft()
+            if not self.past_key_values:
+                self.last_ids = self._start_ids
+            elif int(self.last_ids.reshape(-1)[-1]) == self.eos_token_id and self.last_ids.numel() == 1:
+                self.last_ids = torch.cat([self.last_ids.reshape(1, -1), self._added_stream_prompt_ids], dim=1)
+            dec = self._forward(self.last_ids, frame_embeds)
+            # 2. a query due at this frame's time is answered right after the frame
+            if self.query_queue and video_time >= self.query_queue[0][0]:
+                video_time, query = self.query_queue.popleft()
+                return video_time, query
+            # 3. speak/silent: below-threshold interval probability -> the argmax excludes the interval id
+            next_id = dec.next_id(self.frame_token_interval_id, self.frame_token_interval_threshold)
+            self.last_ids = torch.tensor([[next_id]], dtype=torch.long)
+            if next_id != self.frame_token_interval_id:
+                return video_time, None
+        return None, None
+
+    def __call__(self):
+        while not self.frame_embeds_queue:
+            continue
+        video_time, query = self._call_for_streaming()
+        response = None
+        if video_time is not None:
+            query, response = self._call_for_response(video_time, query)
+        return query, response
+
+
+def _read_video_tchw(path: str) -> torch.Tensor:
+    try:
+        import cv2
+    except Exception as e:  # pragma: no cover
+        raise RuntimeError(f"no video decoder available for {path}: {e}")
+    cap = cv2.VideoCapture(path)
+    frames = []
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        frames.append(torch.from_numpy(cv2.cvtColor(fr, cv2.COLOR_BGR2RGB)).permute(2, 0, 1))
+    cap.release()
+    if not frames:
+        raise RuntimeError(f"could not decode any frame from {path}")
+    return torch.stack(frames)
