@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the per-frame hot path (BASELINE.json metric: streaming frames/sec/GPU, 10 tok/frame,
+~12k-token KV) — driver contract in the task statement.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA engine), one rank per GPU under torchrun
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+
+One *step* = one frame of one video stream through the whole path: SigLIP-L/16-384 ViT -> CLS + 3x3 pooled
+tokens -> connector -> Llama-3-8B KV-append forward over [interval token | 10 frame tokens] on a >=12k-token
+KV cache -> on-device speak/silent decision.  Workload = BASELINE.json configs[1] (1 stream per GPU, 10-min
+video position: kv 12 000 -> 12 000 + 11*steps), synthetic frames and seeded random weights of the
+full-size architecture (no checkpoint/network available).  N GPUs run N independent streams (weights
+broadcast once over NCCL at init, no hot-path collective): "scaling": "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "streaming frames/sec (10 tok/frame, 12k-ctx KV), all GPUs"
+UNIT = "frames/s"
+KV_START = 12000
+WORKLOAD = ("configs[1]: 1 stream/GPU, SigLIP-L/16-384 + Llama-3-8B, frame step of 11 tokens at kv>=12000 "
+            "(10-min video @2FPS position), synthetic 384x384 frames, seeded random weights")
+
+
+# ----------------------------------------------------------------------------- helpers
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1468.8))), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU (reference algorithm) arm
+def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 4, vit_layers: int = 6):
+    """Times the oracle (CPU port of the reference forward, oracle/vlo_oracle.py) on the host cores.
+
+    Bounded sample per step: the full-size ViT trunk truncated to `vit_layers` of 24 blocks (+ embeddings,
+    head, pool) and the full-width decoder truncated to `dec_layers` of 32 layers over a 12k-token cache
+    (+ final norm, lm_head), each scaled to the full layer count -> seconds per full frame step."""
+    import torch
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import vlo_bootstrap  # noqa: F401
+    import vlo_oracle as O
+    from videollm_online_b200 import llama3_8b_siglip_l
+    import dataclasses
+    cfg = llama3_8b_siglip_l()
+    g = torch.Generator().manual_seed(0)
+    H, I, V = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
+    nh, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+
+    def rnd(shape, std=0.02, dtype=torch.bfloat16):
+        n = 1
+        for s in shape:
+            n *= s
+        block = torch.randn(min(n, 1 << 22), generator=g) * std       # tile a 4M-element random block: fast fill
+        reps = (n + block.numel() - 1) // block.numel()
+        return block.repeat(reps)[:n].view(*shape).to(dtype).contiguous()
+
+    # ---- decoder: ONE layer's random weights aliased for every sampled layer (436 MB >> L3, so no cache reuse)
+    layer = {"self_attn.q_proj.weight": rnd((nh * hd, H)), "self_attn.k_proj.weight": rnd((nkv * hd, H)),
+             "self_attn.v_proj.weight": rnd((nkv * hd, H)), "self_attn.o_proj.weight": rnd((H, nh * hd)),
+             "mlp.gate_proj.weight": rnd((I, H)), "mlp.up_proj.weight": rnd((I, H)), "mlp.down_proj.weight": rnd((H, I)),
+             "input_layernorm.weight": torch.ones(H, dtype=torch.bfloat16),
+             "post_attention_layernorm.weight": torch.ones(H, dtype=torch.bfloat16)}
+    sd = {"model.norm.weight": torch.ones(H, dtype=torch.bfloat16), "lm_head.weight": rnd((V, H)),
+          "connector.0.weight": rnd((H, cfg.vision_hidden_size)), "connector.0.bias": rnd((H,)),
+          "connector.2.weight": rnd((H, H)), "connector.2.bias": rnd((H,))}
+    for i in range(dec_layers):
+        for k, v in layer.items():
+            sd[f"model.layers.{i}.{k}"] = v
+    dcfg = dataclasses.replace(cfg, num_hidden_layers=dec_layers)
+    kv_block = rnd((1, nkv, KV_START, hd), 1.0)
+    # ---- ViT: full-size SigLIP-L weights for the sampled blocks (fp32, as on a CPU host)
+    from videollm_online_b200 import weights as W
+    vcfg = dataclasses.replace(cfg, vision_num_hidden_layers=vit_layers)
+    vs = {k: v for k, v in W.synthetic_vision_state(vcfg, seed=1).items()}
+    frames = torch.randint(0, 256, (1, 3, cfg.frame_resolution, cfg.frame_resolution), dtype=torch.uint8, generator=g)
+    ids = torch.tensor([cfg.frame_token_interval_id])
+    sd["model.embed_tokens.weight"] = rnd((1024, H), 1.0)  # only row `interval id` is read
+
+    def one_step():
+        t0 = time.perf_counter()
+        fe = O.visual_embed(sd, vs, vcfg, frames)
+        t1 = time.perf_counter()
+        cache = O.KVCache(dec_layers)
+        for i in range(dec_layers):
+            cache.k[i], cache.v[i] = kv_block, kv_block
+        emb = torch.cat([O.embed_tokens(sd, ids), fe], 0)
+        t2 = time.perf_counter()
+        logits = O.llama_forward(sd, dcfg, emb, cache)
+        O.decide(logits[-1], cfg.frame_token_interval_id, 0.725)
+        t3 = time.perf_counter()
+        return t1 - t0, t3 - t2
+
+    with torch.no_grad():
+        for _ in range(n_warm):
+            one_step()
+        tv, td = [], []
+        for _ in range(n_steps):
+            a, b = one_step()
+            tv.append(a); td.append(b)
+    # scale the truncated stacks to the full model (per-layer cost is uniform; embeddings/head/lm_head are
+    # counted once at full size inside the sample and slightly over-weighted by the scaling -> conservative for us)
+    vit_s = sum(tv) / len(tv) * (cfg.vision_num_hidden_layers / vit_layers)
+    dec_s = sum(td) / len(td) * (cfg.num_hidden_layers / dec_layers)
+    return vit_s + dec_s, {"vit_s_per_frame": vit_s, "decoder_s_per_step": dec_s, "threads": torch.get_num_threads(),
+                           "sample": f"{n_steps} frame steps (+{n_warm} warm-up) of oracle/vlo_oracle.py: full-size SigLIP-L trunk truncated "
+                                     f"to {vit_layers}/24 blocks and Llama-3-8B truncated to {dec_layers}/32 layers at kv={KV_START}, "
+                                     "scaled to the full layer counts; fp32 ViT / bf16 decoder as the reference runs on a CPU host"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    t0 = time.perf_counter()
+    per_step, info = cpu_reference_times(max(1, args.steps), max(0, args.warmup))
+    fps = 1.0 / per_step
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "per-step working set (15 GB weights + 1.6 GB KV) >> cache"},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": info["threads"], "kind": "port", "sample": info["sample"],
+                             "vit_s_per_frame": info["vit_s_per_frame"], "decoder_s_per_step": info["decoder_s_per_step"],
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_engine_arm(args):
+    import torch
+    import vlo_bootstrap  # noqa: F401
+    from videollm_online_b200 import llama3_8b_siglip_l, weights as W
+    from videollm_online_b200.engine import Engine
+    from videollm_online_b200.modeling_live import LiveLlamaForCausalLM
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    cfg = llama3_8b_siglip_l()
+    K, Wm = args.steps, max(3, args.warmup)
+    n_frames = K + Wm + 8
+    cap = ((KV_START + 11 * (2 * n_frames + 8) + 63) // 64) * 64 + 128
+    eng = Engine(cfg, dev, max_streams=1, max_kv_tokens=cap, max_step_tokens=32, max_vit_batch=1)
+
+    # ---- weights: rank 0 synthesises, everyone else receives them over NCCL/NVLink (init only)
+    from videollm_online_b200.dist import broadcast_weights
+    weights = W.synthetic_engine_weights(cfg, dev, cap, seed=0) if rank == 0 else None
+    t_b0 = time.perf_counter()
+    weights = broadcast_weights(cfg, weights, dev, cap, dist)
+    torch.cuda.synchronize()
+    bcast_s = time.perf_counter() - t_b0
+    eng.load_weights(weights)
+    model = LiveLlamaForCausalLM(cfg, eng)
+    sid = eng.stream_open()
+    g = torch.Generator().manual_seed(1234 + rank)
+    S = cfg.frame_resolution
+    frames_host = torch.randint(0, 256, (n_frames, 3, S, S), dtype=torch.uint8, generator=g).pin_memory()
+    frames_dev = frames_host.to(dev)
+    prefix = torch.tensor([cfg.frame_token_interval_id], dtype=torch.int64, device=dev)
+    packed = torch.zeros(11, cfg.hidden_size, dtype=torch.bfloat16, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def frame_step_resident(i):           # inputs already in HBM, no host sync
+        fe = eng.vit_encode(frames_dev[i:i + 1])
+        packed[1:] = fe
+        eng.step([sid], [11], packed, prefix_ids=prefix, want_logits=True)
+
+    fbuf = torch.empty(1, 3, S, S, dtype=torch.uint8, device=dev)
+
+    def frame_step_e2e(i):                # public API with HOST frames: H2D copy in, decision D2H out
+        fbuf.copy_(frames_host[i:i + 1], non_blocking=True)
+        fe = model.visual_embed(fbuf)
+        packed[1:] = fe
+        eng.step([sid], [11], packed, prefix_ids=prefix, want_logits=True)
+        return eng.read_decisions(1)[0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (value)
+    eng.kv_fill_synthetic(sid, KV_START, seed=7 + rank)
+    for i in range(Wm):
+        frame_step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        frame_step_resident(Wm + i)
+    e1.record(stream)
+    barrier()
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    kv_end = eng.kv_len(sid)
+
+    # ---- end-to-end timing through the public API with host frames (e2e)
+    eng.kv_truncate(sid, KV_START)
+    for i in range(Wm):
+        frame_step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        frame_step_e2e(Wm + i)
+    torch.cuda.synchronize()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    barrier()
+
+    # ---- per-kernel-class roofline pass (CUDA events around every launch of the class, same workload)
+    roof = None
+    if rank == 0:
+        eng.kv_truncate(sid, KV_START)
+        eng.lib.vlo_profile_enable(1)
+        P = min(K, 10)
+        for i in range(P):
+            frame_step_resident(Wm + i)
+        ncls = 6
+        ms, n, by = (C.c_double * ncls)(), (C.c_longlong * ncls)(), (C.c_double * ncls)()
+        eng.lib.vlo_profile_read(ms, n, by, ncls)
+        eng.lib.vlo_profile_enable(0)
+        hbm_peak, tf_peak, which = _peaks()
+        names = ["gemm_weight_stream", "attn_kvappend", "attn_merge", "gemm_vit", "vit_attn", "other"]
+        cls = {}
+        for j, nm in enumerate(names):
+            if n[j]:
+                cls[nm] = {"launches_per_step": n[j] / P, "ms_per_step": ms[j] / P, "avg_us_per_launch": 1e3 * ms[j] / n[j],
+                           "algo_gb_per_step": by[j] / P / 1e9, "achieved_gbs": (by[j] / 1e9) / (ms[j] / 1e3) if ms[j] > 0 else None}
+        gs, at = cls.get("gemm_weight_stream"), cls.get("attn_kvappend")
+        roof = {"bound": "hbm", "kernel": "gemm_tn_kernel<bf16, swap-AB> (decoder weight streaming: 15.0 GB of the 16.6 GB/step)",
+                "achieved": gs["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": gs["achieved_gbs"] / hbm_peak,
+                "peak_source": which, "traffic": None,
+                "avg_us_per_launch": gs["avg_us_per_launch"], "launches_per_step": gs["launches_per_step"],
+                "algo_bytes_per_launch": 1e9 * gs["algo_gb_per_step"] / gs["launches_per_step"]}
+        roof_attn = {"bound": "hbm", "kernel": "attn_kvappend_kernel (KV-append attention, one launch per layer)",
+                     "achieved": at["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": at["achieved_gbs"] / hbm_peak,
+                     "peak_source": which, "traffic": None, "avg_us_per_launch": at["avg_us_per_launch"],
+                     "algo_bytes_per_launch": 1e9 * at["algo_gb_per_step"] / at["launches_per_step"]}
+        step_bytes = 15009316864 + (KV_START + 11 * (K // 2)) * 131072
+        roof_step = {"bound": "hbm", "algo_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_total / K / 1e3) / 1e9,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (ms_total / K / 1e3) / 1e9 / hbm_peak}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    fps = world * K / (ms_total / 1e3)
+    e2e_fps = world * K / e2e_s
+    line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "kv_tokens_start": KV_START, "kv_tokens_end": kv_end,
+                       "tokens_per_step": 11, "vit_dtype": "fp16 operands / fp32 accumulate", "parallelism": f"replicas x{world} (weights broadcast at init, no hot-path collective)",
+                       "l2": "inputs larger than L2: every step streams 15.0 GB of weights + 1.6 GB of KV (L2 = 126 MB)",
+                       "weight_broadcast_s": bcast_s},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(3 * S * S + 11 * 4 * 2 + 8), "d2h_bytes_per_step": 32,
+                    "ms_per_step": 1e3 * e2e_s / K, "api": "LiveLlamaForCausalLM.visual_embed + Engine.step (vlo_vit_encode / vlo_step_ids) + read_decisions"},
+            "roofline": roof, "roofline_attn": roof_attn, "roofline_step": roof_step, "kernel_classes": cls}
+    if world == 1 and not args.no_cpu_baseline:
+        per_step, info = cpu_reference_times(2, 1)
+        line["cpu_baseline"] = {"value": 1.0 / per_step, "unit": UNIT, "cores": info["threads"], "kind": "port",
+                                "sample": info["sample"], "host_cpus": os.cpu_count(),
+                                "vit_s_per_frame": info["vit_s_per_frame"], "decoder_s_per_step": info["decoder_s_per_step"]}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_engine_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,14 @@ typedef struct vlo_decision {
 const char* vlo_last_error(void);
 /* number of kernels of this library launched so far in this process (bench: gpu_launches) */
 long long vlo_launch_count(void);
+/* Optional CUDA-event profiler: when enabled every launch of the classes below is bracketed by an event
+ * pair on its stream.  vlo_profile_read synchronises, returns per-class sums since the last read
+ * (milliseconds, launches, algorithmic HBM bytes as defined in DESIGN.md) and resets.
+ * classes: 0 weight-streaming GEMM (decoder/connector/lm_head), 1 KV-append attention, 2 split-KV merge,
+ *          3 ViT GEMM, 4 ViT attention, 5 other. */
+#define VLO_PROF_NUM_CLASSES 6
+int vlo_profile_enable(int on);
+int vlo_profile_read(double* ms, long long* launches, double* algo_bytes, int n_classes);
 /* 1 when the device is an sm_100 part the kernels can run on */
 int vlo_device_supported(int device);
 

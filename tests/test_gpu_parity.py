@@ -26,7 +26,7 @@ def built(tiny):
     from videollm_online_b200.modeling_live import build_live
     cfg, llm, vis = tiny
     model, tok = build_live(config=cfg, llm_state=llm, vision_state=vis, set_vision_inside=True, device="cuda:0",
-                            max_streams=4, max_kv_tokens=1024, max_step_tokens=64, max_vit_batch=4)
+                            max_streams=4, max_kv_tokens=1024, max_step_tokens=128, max_vit_batch=4)
     return model, tok
 
 
@@ -227,7 +227,7 @@ def test_error_paths(built, tiny):
         eng.step([99], [1], torch.zeros(1, cfg.hidden_size, dtype=torch.bfloat16, device="cuda"))
     s = eng.stream_open()
     with pytest.raises(VloError):  # exceeds max_step_tokens
-        eng.step([s], [65], torch.zeros(65, cfg.hidden_size, dtype=torch.bfloat16, device="cuda"))
+        eng.step([s], [129], torch.zeros(129, cfg.hidden_size, dtype=torch.bfloat16, device="cuda"))
     with pytest.raises(VloError):
         eng.vit_encode(torch.zeros(1, 3, 32, 32, dtype=torch.uint8))
     eng.stream_close(s)

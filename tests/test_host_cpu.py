@@ -1,0 +1,153 @@
+"""CPU-side tests: C-ABI surface, host logic, tokenizer/template, weight packing, multi-process plumbing."""
+import ctypes as C
+import os
+import pathlib
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    from videollm_online_b200 import _lib
+    lib = _lib.load()
+    header = (ROOT / "include" / "vlo_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(vlo_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vlo_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_struct_layouts_match_header():
+    from videollm_online_b200._lib import VloConfig, VloDecision
+    assert C.sizeof(VloDecision) == 32
+    assert C.sizeof(VloConfig) == 22 * 4
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    from videollm_online_b200 import VloError, tiny_config
+    from videollm_online_b200.engine import Engine
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(VloError):
+        Engine(tiny_config(), "cuda:0")
+    with pytest.raises(VloError):
+        Engine(tiny_config(), "cpu")
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = ROOT / "videollm-online_b200"
+    for f in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
+        txt = f.read_text(errors="ignore")
+        assert "vlo_oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_chat_template_pieces():
+    from videollm_online_b200 import tiny_config
+    from videollm_online_b200.tokenization_live import ByteTokenizer, render_chat
+    cfg = tiny_config()
+    tok = ByteTokenizer(cfg)
+    kw = dict(bos_token="<B>", eos_token="<E>")
+    assert render_chat([{"role": "system", "content": "S"}], add_stream_prompt=True, **kw) == "<B>S\n\n["
+    assert render_chat([{}], add_stream_prompt=True, **kw) == "\n["
+    assert render_chat([{}], add_stream_generation_prompt=True, **kw) == "]\nAssistant:"
+    assert render_chat([{"role": "user", "content": "Q"}], add_stream_query_prompt=True, add_generation_prompt=True, **kw) == "]\nUser: Q\nAssistant:"
+    conv = [{"role": "system", "content": "S"}, {"role": "stream", "num_frames": 2}, {"role": "user", "content": "Q"},
+            {"role": "assistant", "content": "A"}]
+    ph = lambda n: ",".join(["<v>" * 10] * n)
+    assert render_chat(conv, stream_placeholder=ph, **kw) == "<B>S\n\n[" + "<v>" * 10 + "," + "<v>" * 10 + "]\nUser: Q\nAssistant: A<E>"
+    ids = tok.apply_chat_template([{}], add_stream_generation_prompt=True)
+    assert ids[0] == cfg.stream_end_id                      # "]\n" is ONE id, as demo/inference.py:44 assumes
+    assert tok.encode(",") == [cfg.frame_token_interval_id]
+    assert tok.decode(tok.encode("hello, wörld")) == "hello, wörld"
+
+
+def test_parse_args_two_pass_presets():
+    from videollm_online_b200.config import parse_args
+    a = parse_args([])
+    assert (a.live_version, a.frame_num_tokens, a.frame_token_pooled, a.frame_token_interval, a.max_num_frames) == ("live1+", 10, [3, 3], ",", 1200)
+    b = parse_args(["--live_version", "live1", "--frame_fps", "10"])
+    assert (b.frame_num_tokens, b.frame_token_pooled, b.frame_token_interval, b.max_num_frames, b.frame_fps) == (1, None, "", 7200, 10)
+
+
+def test_pack_layout_and_lora_merge():
+    from videollm_online_b200 import tiny_config, weights as W
+    from videollm_online_b200.dist import engine_weight_spec
+    cfg = tiny_config()
+    sd, vs = W.synthetic_llm_state(cfg), W.synthetic_vision_state(cfg)
+    packed = W.pack_llm_for_engine(cfg, sd, "cpu", 256)
+    packed.update(W.pack_vision_for_engine(cfg, vs, "cpu"))
+    spec = engine_weight_spec(cfg, 256)
+    assert set(spec) == set(packed)
+    for k, (shape, dt) in spec.items():
+        assert tuple(packed[k].shape) == tuple(shape) and packed[k].dtype == dt, k
+    assert torch.equal(packed["L0.qkv"][: cfg.num_attention_heads * 128], sd["model.layers.0.self_attn.q_proj.weight"])
+    assert torch.equal(packed["L1.gate_up"][cfg.intermediate_size:], sd["model.layers.1.mlp.up_proj.weight"])
+    # LoRA merge == unmerged forward (y = W x + 2 B A x) up to bf16 rounding of the merged weight
+    g = torch.Generator().manual_seed(0)
+    r = 8
+    key = "model.layers.0.self_attn.q_proj"
+    A = (torch.randn(r, cfg.hidden_size, generator=g) * 0.05).bfloat16()
+    B = (torch.randn(cfg.num_attention_heads * 128, r, generator=g) * 0.05).bfloat16()
+    merged = W.merge_lora(sd, {f"base_model.model.{key}.lora_A.default.weight": A, f"base_model.model.{key}.lora_B.default.weight": B,
+                               "base_model.model.connector.modules_to_save.default.0.bias": torch.ones(cfg.hidden_size)},
+                          lora_alpha=16, lora_r=r)
+    x = torch.randn(5, cfg.hidden_size, generator=g)
+    want = x @ sd[key + ".weight"].float().t() + 2.0 * (x @ A.float().t()) @ B.float().t()
+    got = x @ merged[key + ".weight"].float().t()
+    assert (got - want).abs().max() < 0.05 * want.abs().max()
+    assert torch.equal(merged["connector.0.bias"], torch.ones(cfg.hidden_size, dtype=torch.bfloat16))
+
+
+def test_rope_tables_match_hf_formula():
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import vlo_oracle as O
+    from videollm_online_b200 import tiny_config, weights as W
+    cfg = tiny_config()
+    cos, sin = W.rope_tables(cfg, 300, "cpu")
+    c2, s2 = O.rope_cos_sin(cfg, torch.arange(300)[None], torch.bfloat16)
+    assert torch.equal(cos, c2[0, :, :64]) and torch.equal(sin, s2[0, :, :64])
+    assert torch.equal(c2[0, :, :64], c2[0, :, 64:])
+
+
+def test_decision_threshold_semantics():
+    from videollm_online_b200.engine import Decision
+    row_i = torch.tensor([7, 9, 0, 0, 0, 0, 7, 0], dtype=torch.int32)
+    f = row_i.view(torch.float32).clone()
+    f[2] = 0.7265625            # bf16 value just above 0.725: torch compares against bf16(0.725) = 0.7265625
+    d = Decision(row_i, f)
+    assert d.next_id(7, 0.725) == 7 and d.next_id(7, 0.727) == 7 and d.next_id(7, 0.74) == 9
+
+
+@pytest.mark.timeout(180)
+def test_weight_broadcast_two_ranks_gloo(tmp_path):
+    """N>1 plumbing on CPU: rank 0 owns the weights, rank 1 receives identical tensors (gloo, 127.0.0.1)."""
+    script = tmp_path / "bc.py"
+    script.write_text(f"""
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, {str(ROOT)!r})
+import vlo_bootstrap
+from videollm_online_b200 import tiny_config, weights as W
+from videollm_online_b200.dist import broadcast_weights
+dist.init_process_group('gloo')
+cfg = tiny_config()
+full = W.pack_llm_for_engine(cfg, W.synthetic_llm_state(cfg), 'cpu', 128)
+full.update(W.pack_vision_for_engine(cfg, W.synthetic_vision_state(cfg), 'cpu'))
+got = broadcast_weights(cfg, full if dist.get_rank() == 0 else None, 'cpu', 128, dist)
+assert set(got) == set(full) and all(torch.equal(got[k], full[k]) for k in full)
+# static stream -> rank assignment: round-robin, every stream owned by exactly one rank
+streams = list(range(5)); mine = [s for s in streams if s % dist.get_world_size() == dist.get_rank()]
+cnt = torch.tensor([len(mine)]); dist.all_reduce(cnt); assert int(cnt) == 5
+print('rank', dist.get_rank(), 'ok')
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", str(script)], capture_output=True, text=True, env=env, timeout=170)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

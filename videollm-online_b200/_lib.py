@@ -48,6 +48,8 @@ SIGNATURES = {
     "vlo_last_error": (C.c_char_p, []),
     "vlo_launch_count": (_LL, []),
     "vlo_device_supported": (_I, [_I]),
+    "vlo_profile_enable": (_I, [_I]),
+    "vlo_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(_LL), C.POINTER(C.c_double), _I]),
     "vlo_engine_create": (_I, [C.POINTER(VloConfig), _I, C.POINTER(_P)]),
     "vlo_engine_destroy": (_I, [_P]),
     "vlo_load_tensor": (_I, [_P, C.c_char_p, _P, C.c_int64]),

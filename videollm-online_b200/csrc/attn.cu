@@ -70,6 +70,11 @@ int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, in
   const int want = std::max(1, kNumSMs / (n_kv_heads * n_items));
   int max_splits = 1;
   size_t slots = 0;
+  double algo = 0.0;
+  for (const AttnItem& it : items)  // K+V rows read once per item, Q read, output written
+    algo += static_cast<double>(it.q_pos0 + it.q_count) * n_kv_heads * kAttnHD * 2 * 2 +
+            static_cast<double>(it.q_count) * n_heads * kAttnHD * 2 * 2;
+  plan->algo_bytes = algo;
   for (AttnItem& it : items) {
     const int nblk = (it.q_pos0 + it.q_count + kAttnBlk - 1) / kAttnBlk;
     int bps = (nblk + want - 1) / want;
@@ -126,7 +131,9 @@ int attn_run(const AttnPlan& plan, const void* d_q, const void* d_k, const void*
   p.n_heads = n_heads;
   p.n_kv_heads = n_kv_heads;
   p.scale_log2 = scale_log2;
+  prof_begin(PROF_ATTN, stream, plan.algo_bytes);
   attn_kvappend_kernel<<<dim3(plan.max_splits, n_kv_heads, plan.n_items), kAttnThreads, kAttnSmemBytes, stream>>>(tk, tv, p);
+  prof_end(stream);
   VLO_LAUNCH_CHECK();
   AttnMergeParams mp{};
   mp.ws_o = plan.ws_o;
@@ -137,7 +144,9 @@ int attn_run(const AttnPlan& plan, const void* d_q, const void* d_k, const void*
   mp.n_heads = n_heads;
   mp.n_kv_heads = n_kv_heads;
   mp.scale_log2 = scale_log2;
+  prof_begin(PROF_ATTN_MERGE, stream, 0.0);
   attn_merge_kernel<<<dim3(n_heads, plan.total_tokens), 128, 0, stream>>>(mp);
+  prof_end(stream);
   VLO_LAUNCH_CHECK();
   count_launch(2);
   return 0;

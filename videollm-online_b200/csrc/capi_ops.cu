@@ -12,6 +12,14 @@ const char* vlo_last_error(void) { return last_error(); }
 
 long long vlo_launch_count(void) { return launch_count(); }
 
+int vlo_profile_enable(int on) {
+  prof_enable(on != 0);
+  return 0;
+}
+int vlo_profile_read(double* ms, long long* launches, double* algo_bytes, int n_classes) {
+  return prof_read(ms, launches, algo_bytes, n_classes);
+}
+
 int vlo_device_supported(int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {

@@ -37,6 +37,22 @@ int fail(const std::string& msg);  // set_error + return -1
 void count_launch(int n = 1);
 long long launch_count();
 
+// ---- per-kernel-class event profiler (runtime.cu); classes are indices into vlo_profile_read's arrays
+enum ProfClass : int {
+  PROF_GEMM_STREAM = 0,  // swap-AB weight-streaming GEMMs (decoder, connector, lm_head)
+  PROF_ATTN = 1,         // attn_kvappend_kernel (the KV-append attention main kernel)
+  PROF_ATTN_MERGE = 2,   // split-KV merge
+  PROF_GEMM_VIT = 3,     // ViT trunk GEMMs (activations on MMA-M)
+  PROF_VIT_ATTN = 4,
+  PROF_OTHER = 5,
+  PROF_NUM = 6,
+};
+void prof_enable(bool on);
+bool prof_on();
+void prof_begin(int cls, cudaStream_t st, double algo_bytes);
+void prof_end(cudaStream_t st);
+int prof_read(double* ms, long long* n, double* bytes, int ncls);
+
 // ---- GEMM (gemm.cu) ---------------------------------------------------------------
 struct GemmCall {
   int fmt;   // 0 fp16, 1 bf16
@@ -78,6 +94,7 @@ struct AttnPlan {
   void* d_items;
   int* d_tok_item;
   int n_items, max_splits, total_tokens;
+  double algo_bytes;  // algorithmic HBM bytes of one attn_run over this plan (K+V rows read, Q read, out written)
 };
 // Build the work-item plan on the host and enqueue its upload.  h_stage (>= attn_stage_bytes())
 // must stay untouched until the copies enqueued on `stream` have run.

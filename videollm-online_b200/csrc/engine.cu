@@ -543,8 +543,10 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     VLO_LAUNCH_CHECK();
     if (gemm_store16(FMT_F16, 0, e->v_xn, rows, v.qkv_w, 3 * C, C, e->v_qkv, 3 * C, v.qkv_b, ACT_NONE, vit_bn(rows, 3 * C), st))
       return -1;
+    prof_begin(PROF_VIT_ATTN, st, 4.0 * rows * C * 2);
     vit_attn_kernel<<<dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), kVitThreads, kVitSmemBytes, st>>>(
         tm_qkv, e->v_attn, P, C, scale_log2);
+    prof_end(st);
     VLO_LAUNCH_CHECK();
     if (resid_gemm(e->v_attn, v.out_w, v.out_b, C)) return -1;
     layernorm_kernel<float><<<rows, 256, ln_smem, st>>>(e->v_h, v.ln2_w, v.ln2_b, e->v_xn, nullptr, C, c.vit_ln_eps);

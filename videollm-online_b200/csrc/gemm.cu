@@ -95,7 +95,14 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& arg
                                   GemmCfg<BN>::kSmemBytes));
     attr_set = true;
   }
+  if (prof_on()) {
+    const double esz = (EPI == EPI_STORE16) ? 2.0 : 4.0;
+    const double bytes = 2.0 * args.k * (static_cast<double>(args.rows_a) + args.rows_b) +
+                         esz * static_cast<double>(args.rows_a) * args.rows_b * (EPI == EPI_PARTIAL ? grid.z : 1);
+    prof_begin(SWAP ? PROF_GEMM_STREAM : PROF_GEMM_VIT, stream, bytes);
+  }
   kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, args);
+  prof_end(stream);
   VLO_LAUNCH_CHECK();
   count_launch();
   return 0;
