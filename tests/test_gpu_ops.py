@@ -131,3 +131,59 @@ def test_attention_is_a_convex_combination_at_full_size(lib):
     check(lib.vlo_op_attn_kvappend(p(q), p(k), p(v), p(out), p(ws), n_tok, H, Hk, D, kv_len, stride, st), "attn")
     torch.cuda.synchronize()
     assert (out.float() - 0.5).abs().max() < 4e-3
+
+
+def _py_sk_planes(rows_w, k, G):
+    tiles, kb = (rows_w + 127) // 128, k // 64
+    U = tiles * kb
+    lo = lambda c: (c * U) // G
+    def owner(u):
+        c = min((u * G) // U, G - 1)
+        while lo(c + 1) <= u:
+            c += 1
+        while c > 0 and lo(c) > u:
+            c -= 1
+        return c
+    return [owner((t + 1) * kb - 1) - owner(t * kb) + 1 for t in range(tiles)]
+
+
+@pytest.mark.parametrize("T,N,K,G", [(11, 6144, 4096, 0), (11, 4096, 14336, 0), (11, 28672, 4096, 0), (1, 512, 256, 0),
+                                     (33, 1000, 1024, 7), (128, 640, 4096, 148), (11, 256, 128, 148)])
+def test_gemm_ws_streamk_partials(lib, T, N, K, G):
+    """persistent stream-K weight-streaming GEMM: planes sum to X W^T; decomposition covers every unit once"""
+    from videollm_online_b200._lib import check
+    torch.manual_seed(N + T)
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    x = torch.randn(T, K, device="cuda").bfloat16()
+    planes = C.c_int(0)
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.vlo_op_gemm_ws(1, 0, p(w), N, p(x), T, K, None, N, T * N, None, 0, G, C.byref(planes), st), "plan")
+    ws = torch.zeros(planes.value, T, N, device="cuda")
+    check(lib.vlo_op_gemm_ws(1, 0, p(w), N, p(x), T, K, p(ws), N, T * N, None, 0, G, C.byref(planes), st), "gemm_ws")
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t()
+    assert (ws.sum(0) - ref).abs().max() <= 2e-3 * ref.abs().max()
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    Gs = min(G if G > 0 else n_sm, ((N + 127) // 128) * (K // 64))
+    assert max(_py_sk_planes(N, K, Gs)) == planes.value
+
+
+@pytest.mark.parametrize("T,N,K,act", [(8, 128256, 4096, 0), (40, 4096, 1024, 2), (128, 1000, 512, 0), (3, 256, 64, 1)])
+def test_gemm_ws_tiles_store16(lib, T, N, K, act):
+    from videollm_online_b200._lib import check
+    torch.manual_seed(T)
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    x = torch.randn(T, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    out = torch.zeros(T, N, device="cuda", dtype=torch.bfloat16)
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.vlo_op_gemm_ws(1, 1, p(w), N, p(x), T, K, p(out), N, 0, p(bias), act, 0, None, st), "gemm_ws")
+    torch.cuda.synchronize()
+    y = (x.float() @ w.float().t() + bias).bfloat16()
+    if act == 2:
+        y = y * 0.5 * (1.0 + torch.erf(y / math.sqrt(2.0)))
+    elif act == 1:
+        y = torch.nn.functional.gelu(y.float(), approximate="tanh").bfloat16()
+    assert (out.float() - y.float()).abs().max() <= 1e-2 * y.float().abs().max()

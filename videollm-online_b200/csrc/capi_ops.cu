@@ -60,6 +60,29 @@ int vlo_op_gemm(int fmt, int swap, int epi, int act, const void* d_a, int rows_a
 
 extern "C" {
 
+int vlo_op_gemm_ws(int fmt, int mode, const void* d_w, int rows_w, const void* d_x, int rows_x, int k, void* d_out,
+                   int ld_out, long long plane_stride, const float* d_bias, int act, int n_ctas, int* h_max_planes,
+                   void* cuda_stream) {
+  GemmWsCall c{};
+  c.fmt = fmt;
+  c.mode = mode;
+  c.w = d_w;
+  c.rows_w = rows_w;
+  c.x = d_x;
+  c.rows_x = rows_x;
+  c.k = k;
+  c.out = d_out;
+  c.ld_out = ld_out;
+  c.plane_stride = plane_stride;
+  c.bias = d_bias;
+  c.act = act;
+  int planes = 1;
+  gemm_ws_plan(rows_w, k, mode, n_ctas, &c.sk, &planes);
+  if (h_max_planes) *h_max_planes = planes;
+  if (d_out == nullptr) return 0;  // planning query only
+  return gemm_ws_launch(c, static_cast<cudaStream_t>(cuda_stream));
+}
+
 int64_t vlo_op_attn_ws_bytes(int n_tok, int n_heads, int head_dim, int kv_len) {
   (void)head_dim;
   (void)kv_len;

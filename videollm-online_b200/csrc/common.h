@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <string>
 
+#include "streamk.h"
+
 namespace vlo {
 
 // ---- error plumbing: every C-ABI entry returns 0 / negative and leaves a message here.
@@ -76,6 +78,26 @@ struct GemmCall {
 };
 int gemm_launch(const GemmCall& c, cudaStream_t stream);
 int gemm_fix_splits(int k, int want);
+
+// ---- persistent weight-streaming GEMM (gemm_ws.cuh / gemm.cu)
+struct GemmWsCall {
+  int fmt;            // 0 fp16, 1 bf16
+  int mode;           // 0 stream-K fp32 partial planes, 1 whole tiles + 16-bit epilogue
+  const void* w;      // [rows_w, k]
+  int rows_w;
+  const void* x;      // [rows_x, k], rows_x <= 128
+  int rows_x;
+  int k;
+  void* out;
+  int ld_out;
+  long long plane_stride;
+  const float* bias;
+  int act;
+  SkInfo sk;          // from gemm_ws_plan
+};
+// decomposition for (rows_w, k): n_ctas <= 0 -> one CTA per SM; max_planes = fp32 planes the partials need
+int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_planes);
+int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream);
 
 // ---- attention (attn.cu) ------------------------------------------------------------
 struct AttnSeq {

@@ -3,6 +3,7 @@
 // reference forward is the accumulation order inside the GEMMs and the attention.
 #pragma once
 #include "ptx.cuh"
+#include "streamk.h"
 
 namespace vlo {
 
@@ -34,8 +35,9 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // grid = T rows, block = 256.
 struct ResidNormParams {
   const float* part;
-  int n_splits;
+  int n_splits;             // 0: no partials; > 0: that many planes; < 0: stream-K planes per 128-column tile (sk)
   long long split_stride;
+  SkInfo sk;
   __nv_bfloat16* h;         // [T, H] residual stream, updated in place
   const __nv_bfloat16* w;   // [H] norm weight
   __nv_bfloat16* xn;        // [T, H] normalised output (may be null)
@@ -53,10 +55,11 @@ __global__ void __launch_bounds__(256) resid_rmsnorm_kernel(const ResidNormParam
   float ss = 0.f;
   for (int i = threadIdx.x * 2; i < p.H; i += blockDim.x * 2) {
     float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(h + i));
-    if (p.n_splits > 0) {
+    if (p.n_splits != 0) {
       float y0 = 0.f, y1 = 0.f;
       const float* pp = p.part + static_cast<size_t>(t) * p.H + i;
-      for (int s = 0; s < p.n_splits; ++s) {
+      const int ns = p.n_splits > 0 ? p.n_splits : sk_planes(i >> 7, p.sk);
+      for (int s = 0; s < ns; ++s) {
         const float2 a = *reinterpret_cast<const float2*>(pp + s * p.split_stride);
         y0 += a.x;
         y1 += a.y;
@@ -92,8 +95,9 @@ __global__ void __launch_bounds__(256) resid_rmsnorm_kernel(const ResidNormParam
 // grid = (T, n_heads + 2*n_kv_heads), block = 64 (thread d handles dims d and d+64).
 struct QkvRopeParams {
   const float* part;       // [S][T][(nh + 2 nkv) * 128]
-  int n_splits;
+  int n_splits;            // > 0 planes, < 0 stream-K (head hh == weight tile hh)
   long long split_stride;
+  SkInfo sk;
   const __nv_bfloat16* cos_tab;
   const __nv_bfloat16* sin_tab;
   const int* tok_pos;      // [T] absolute position of the token in its stream
@@ -110,7 +114,8 @@ __global__ void __launch_bounds__(64) qkv_rope_append_kernel(const QkvRopeParams
   const int width = (p.n_heads + 2 * p.n_kv_heads) * 128;
   const float* pp = p.part + static_cast<size_t>(t) * width + hh * 128 + d;
   float x1 = 0.f, x2 = 0.f;
-  for (int s = 0; s < p.n_splits; ++s) {
+  const int ns = p.n_splits > 0 ? p.n_splits : sk_planes(hh, p.sk);
+  for (int s = 0; s < ns; ++s) {
     x1 += pp[s * p.split_stride];
     x2 += pp[s * p.split_stride + 64];
   }
@@ -142,8 +147,9 @@ __global__ void __launch_bounds__(64) qkv_rope_append_kernel(const QkvRopeParams
 // part columns [0, I) = gate, [I, 2I) = up.   grid-stride over T*I/2 pairs.
 struct SwigluParams {
   const float* part;
-  int n_splits;
+  int n_splits;  // > 0 planes, < 0 stream-K
   long long split_stride;
+  SkInfo sk;
   __nv_bfloat16* act;  // [T, I]
   int T, I;
 };
@@ -155,10 +161,15 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const SwigluParams p) {
     const int t = static_cast<int>(e / p.I), i = static_cast<int>(e % p.I);
     const float* pg = p.part + static_cast<size_t>(t) * 2 * p.I + i;
     float g0 = 0.f, g1 = 0.f, u0 = 0.f, u1 = 0.f;
-    for (int s = 0; s < p.n_splits; ++s) {
+    const int ng = p.n_splits > 0 ? p.n_splits : sk_planes(i >> 7, p.sk);
+    const int nu = p.n_splits > 0 ? p.n_splits : sk_planes((p.I + i) >> 7, p.sk);
+    for (int s = 0; s < ng; ++s) {
       const float2 g = *reinterpret_cast<const float2*>(pg + s * p.split_stride);
+      g0 += g.x; g1 += g.y;
+    }
+    for (int s = 0; s < nu; ++s) {
       const float2 u = *reinterpret_cast<const float2*>(pg + s * p.split_stride + p.I);
-      g0 += g.x; g1 += g.y; u0 += u.x; u1 += u.y;
+      u0 += u.x; u1 += u.y;
     }
     g0 = bf16_round(g0); g1 = bf16_round(g1); u0 = bf16_round(u0); u1 = bf16_round(u1);
     const float a0 = bf16_round(g0 / (1.0f + expf(-g0)));

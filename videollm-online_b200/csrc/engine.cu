@@ -112,52 +112,45 @@ int lookup(vlo_engine* e, const std::string& name, int64_t expect_elems, const T
   return 0;
 }
 
-// split-K factor: fill the 148 SMs in whole waves (one CTA per SM) with >= 4 k-blocks per split.
-int choose_splits(int tiles, int k) {
-  const int total_kb = k / kGemmBK;
-  int best = 1;
-  double best_eff = 0.0;
-  for (int s = 1; s <= 16; ++s) {
-    const int fs = gemm_fix_splits(k, s);
-    if (fs != s) continue;
-    if (total_kb / s < 4 && s > 1) break;
-    const int ctas = tiles * s;
-    const int waves = (ctas + kNumSMs - 1) / kNumSMs;
-    const double eff = static_cast<double>(ctas) / (waves * kNumSMs);
-    if (eff > best_eff + 0.03) {
-      best_eff = eff;
-      best = s;
-    }
-  }
-  return best;
-}
-
 int swap_bn(int rows_b) { return rows_b <= 16 ? 16 : (rows_b <= 32 ? 32 : (rows_b <= 64 ? 64 : 128)); }
 
-// weights [n_out, k] x tokens [T, k] -> fp32 partials [S][T][n_out] in e->part; returns S
-int gemm_partial(vlo_engine* e, const bf16* w, int n_out, const bf16* x, int T, int k, int* out_splits,
-                 cudaStream_t st) {
-  const int bn = swap_bn(T);
-  const int tiles = ((n_out + kGemmBM - 1) / kGemmBM) * ((T + bn - 1) / bn);
-  const int S = choose_splits(tiles, k);
-  VLO_CHECK(static_cast<size_t>(S) * T * n_out <= e->part_elems, "split-K workspace too small");
-  GemmCall c{};
+// weights [n_out, k] x tokens [T, k] -> stream-K fp32 partial planes in e->part (persistent kernel)
+int gemm_partial(vlo_engine* e, const bf16* w, int n_out, const bf16* x, int T, int k, SkInfo* sk, cudaStream_t st) {
+  int planes = 1;
+  gemm_ws_plan(n_out, k, 0, 0, sk, &planes);
+  VLO_CHECK(static_cast<size_t>(planes) * T * n_out <= e->part_elems, "stream-K workspace too small");
+  GemmWsCall c{};
   c.fmt = FMT_BF16;
-  c.swap = 1;
-  c.epi = EPI_PARTIAL;
-  c.a = w;
-  c.rows_a = n_out;
-  c.b = x;
-  c.rows_b = T;
+  c.mode = 0;
+  c.w = w;
+  c.rows_w = n_out;
+  c.x = x;
+  c.rows_x = T;
   c.k = k;
   c.out = e->part;
   c.ld_out = n_out;
-  c.splits = S;
-  c.split_stride = static_cast<long long>(T) * n_out;
-  c.stream_weights = 1;
-  c.bn = bn;
-  *out_splits = S;
-  return gemm_launch(c, st);
+  c.plane_stride = static_cast<long long>(T) * n_out;
+  c.sk = *sk;
+  return gemm_ws_launch(c, st);
+}
+
+// whole-tile persistent GEMM with the 16-bit epilogue: out[T, n_out] = act(x W^T + bias)
+int gemm_ws_store16(int fmt, const void* w, int n_out, const void* x, int T, int k, void* out, int ld, const float* bias,
+                    int act, cudaStream_t st) {
+  GemmWsCall c{};
+  c.fmt = fmt;
+  c.mode = 1;
+  c.w = w;
+  c.rows_w = n_out;
+  c.x = x;
+  c.rows_x = T;
+  c.k = k;
+  c.out = out;
+  c.ld_out = ld;
+  c.bias = bias;
+  c.act = act;
+  gemm_ws_plan(n_out, k, 1, 0, &c.sk, nullptr);
+  return gemm_ws_launch(c, st);
 }
 
 int gemm_store16(int fmt, int swap, const void* a, int rows_a, const void* b, int rows_b, int k, void* out, int ld,
@@ -229,6 +222,7 @@ int vlo_engine_create(const vlo_config* cfg, int device, vlo_engine** out) {
   VLO_CHECK(c.hidden_size % 64 == 0 && c.intermediate_size % 64 == 0, "hidden/intermediate must be multiples of 64");
   VLO_CHECK(c.num_heads % c.num_kv_heads == 0, "num_heads % num_kv_heads");
   VLO_CHECK(c.max_streams >= 1 && c.max_kv_tokens >= 64 && c.max_step_tokens >= 1, "capacities");
+  VLO_CHECK(c.max_step_tokens <= 128, "max_step_tokens <= 128 (longer inputs are chunked by the host; chunked == one pass)");
   VLO_CHECK(c.vit_layers == 0 || (c.vit_hidden % 64 == 0 && c.vit_hidden / c.vit_heads == 64 && c.vit_mlp % 64 == 0),
             "vision tower: hidden % 64, head_dim == 64");
   VLO_CHECK(c.vit_layers == 0 || (c.image_size % c.patch_size == 0 && (3 * c.patch_size * c.patch_size) % 64 == 0 &&
@@ -260,7 +254,7 @@ int vlo_engine_create(const vlo_config* cfg, int device, vlo_engine** out) {
   if (dev_alloc_t(e, &e->logits, static_cast<size_t>(c.max_streams) * c.vocab_size)) return -1;
   if (dev_alloc_t(e, &e->decisions, static_cast<size_t>(c.max_streams))) return -1;
   const int widest = std::max(std::max(e->qkv_width, 2 * c.intermediate_size), H);
-  e->part_elems = static_cast<size_t>(16) * T * widest;
+  e->part_elems = static_cast<size_t>(8) * T * widest;  // stream-K needs <= kb/floor(U/G) + 2 planes (<= 4 in practice)
   if (dev_alloc_t(e, &e->part, e->part_elems)) return -1;
   const size_t aws = attn_ws_bytes(T, c.max_streams, c.num_heads, c.num_kv_heads);
   if (dev_alloc(e, reinterpret_cast<void**>(&e->attn_ws), aws, false)) return -1;
@@ -471,11 +465,18 @@ int vlo_connector(vlo_engine* e, const void* d_tokens, int n_rows, void* d_out, 
   VLO_CHECK(n_rows > 0 && n_rows <= cap, "connector: n_rows exceeds max_vit_batch * frame_num_tokens");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   // Linear -> GELU (python erf form, bf16) -> Linear   (models/live_llama/modeling_live_llama.py:18-22)
-  if (gemm_store16(FMT_BF16, 1, e->conn0_w, c.hidden_size, d_tokens, n_rows, c.vit_hidden, e->conn_mid, c.hidden_size,
-                   e->conn0_b, ACT_GELU_ERF_PY, swap_bn(n_rows), st))
-    return -1;
-  return gemm_store16(FMT_BF16, 1, e->conn2_w, c.hidden_size, e->conn_mid, n_rows, c.hidden_size, d_out, c.hidden_size,
-                      e->conn2_b, ACT_NONE, swap_bn(n_rows), st);
+  const bf16* tok = static_cast<const bf16*>(d_tokens);
+  bf16* outp = static_cast<bf16*>(d_out);
+  for (int r0 = 0; r0 < n_rows; r0 += 128) {  // the persistent kernel takes <= 128 token rows per launch
+    const int nr = std::min(128, n_rows - r0);
+    if (gemm_ws_store16(FMT_BF16, e->conn0_w, c.hidden_size, tok + static_cast<size_t>(r0) * c.vit_hidden, nr, c.vit_hidden,
+                        e->conn_mid, c.hidden_size, e->conn0_b, ACT_GELU_ERF_PY, st))
+      return -1;
+    if (gemm_ws_store16(FMT_BF16, e->conn2_w, c.hidden_size, e->conn_mid, nr, c.hidden_size,
+                        outp + static_cast<size_t>(r0) * c.hidden_size, c.hidden_size, e->conn2_b, ACT_NONE, st))
+      return -1;
+  }
+  return 0;
 }
 
 int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, float* d_vit_tokens, void* cuda_stream) {
@@ -576,11 +577,12 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
       return -1;
     probe_attn_kernel<<<dim3(c.vit_heads, B), 128, static_cast<size_t>(P) * sizeof(float), st>>>(e->v_qkv, e->head_q, e->v_pa, P, C, 0.125f);
     VLO_LAUNCH_CHECK();
-    if (gemm_store16(FMT_F16, 1, e->head_out_w, C, e->v_pa, B, C, e->v_resid, C, e->head_out_b, ACT_NONE, swap_bn(B), st)) return -1;
+    VLO_CHECK(B <= 128, "MAP head handles <= 128 frames per call");
+    if (gemm_ws_store16(FMT_F16, e->head_out_w, C, e->v_pa, B, C, e->v_resid, C, e->head_out_b, ACT_NONE, st)) return -1;
     layernorm_kernel<__half><<<B, 256, ln_smem, st>>>(e->v_resid, e->head_ln_w, e->head_ln_b, e->v_lnh, nullptr, C, c.vit_ln_eps);
     VLO_LAUNCH_CHECK();
-    if (gemm_store16(FMT_F16, 1, e->head_fc1_w, M, e->v_lnh, B, C, e->v_m1, M, e->head_fc1_b, ACT_GELU_TANH, swap_bn(B), st)) return -1;
-    if (gemm_store16(FMT_F16, 1, e->head_fc2_w, C, e->v_m1, B, M, e->v_m2, C, e->head_fc2_b, ACT_NONE, swap_bn(B), st)) return -1;
+    if (gemm_ws_store16(FMT_F16, e->head_fc1_w, M, e->v_lnh, B, C, e->v_m1, M, e->head_fc1_b, ACT_GELU_TANH, st)) return -1;
+    if (gemm_ws_store16(FMT_F16, e->head_fc2_w, C, e->v_m1, B, M, e->v_m2, C, e->head_fc2_b, ACT_NONE, st)) return -1;
     cls_residual_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(e->v_resid, e->v_m2, e->tokens32, B, C, NT);
     VLO_LAUNCH_CHECK();
     count_launch(3);
@@ -672,10 +674,11 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
   }
 
   const size_t norm_smem = static_cast<size_t>(H) * sizeof(float);
-  auto resid_norm = [&](int n_splits, long long split_stride, const bf16* w, bool last) -> int {
+  auto resid_norm = [&](const SkInfo* sk, long long split_stride, const bf16* w, bool last) -> int {
     ResidNormParams p{};
     p.part = e->part;
-    p.n_splits = n_splits;
+    p.n_splits = sk ? -1 : 0;
+    if (sk) p.sk = *sk;
     p.split_stride = split_stride;
     p.h = e->h;
     p.w = w;
@@ -690,17 +693,18 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
     return 0;
   };
 
-  if (resid_norm(0, 0, e->dec[0].in_norm, false)) return -1;
+  if (resid_norm(nullptr, 0, e->dec[0].in_norm, false)) return -1;
   const int attn_width = c.num_heads * c.head_dim;
   for (int l = 0; l < c.num_layers; ++l) {
     const DecLayer& d = e->dec[l];
-    int S = 1;
+    SkInfo sk{};
     // fused q|k|v projection -> partials; fix-up + RoPE + in-place KV append
-    if (gemm_partial(e, d.qkv, e->qkv_width, e->xn, T, H, &S, st)) return -1;
+    if (gemm_partial(e, d.qkv, e->qkv_width, e->xn, T, H, &sk, st)) return -1;
     {
       QkvRopeParams p{};
       p.part = e->part;
-      p.n_splits = S;
+      p.n_splits = -1;
+      p.sk = sk;
       p.split_stride = static_cast<long long>(T) * e->qkv_width;
       p.cos_tab = e->rope_cos;
       p.sin_tab = e->rope_sin;
@@ -719,13 +723,14 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
     if (attn_run(plan, e->q, kv_layer_base(e, l, 0), kv_layer_base(e, l, 1), kv_rows_per_layer(c), e->attn_out,
                  c.num_heads, c.num_kv_heads, c.head_dim, st))
       return -1;
-    if (gemm_partial(e, d.o, H, e->attn_out, T, attn_width, &S, st)) return -1;
-    if (resid_norm(S, static_cast<long long>(T) * H, d.post_norm, false)) return -1;
-    if (gemm_partial(e, d.gate_up, 2 * c.intermediate_size, e->xn, T, H, &S, st)) return -1;
+    if (gemm_partial(e, d.o, H, e->attn_out, T, attn_width, &sk, st)) return -1;
+    if (resid_norm(&sk, static_cast<long long>(T) * H, d.post_norm, false)) return -1;
+    if (gemm_partial(e, d.gate_up, 2 * c.intermediate_size, e->xn, T, H, &sk, st)) return -1;
     {
       SwigluParams p{};
       p.part = e->part;
-      p.n_splits = S;
+      p.n_splits = -1;
+      p.sk = sk;
       p.split_stride = static_cast<long long>(T) * 2 * c.intermediate_size;
       p.act = e->act;
       p.T = T;
@@ -735,14 +740,13 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
       VLO_LAUNCH_CHECK();
       count_launch();
     }
-    if (gemm_partial(e, d.down, H, e->act, T, c.intermediate_size, &S, st)) return -1;
+    if (gemm_partial(e, d.down, H, e->act, T, c.intermediate_size, &sk, st)) return -1;
     const bool is_last = (l == c.num_layers - 1);
-    if (resid_norm(S, static_cast<long long>(T) * H, is_last ? e->final_norm : e->dec[l + 1].in_norm, is_last)) return -1;
+    if (resid_norm(&sk, static_cast<long long>(T) * H, is_last ? e->final_norm : e->dec[l + 1].in_norm, is_last)) return -1;
   }
   // ---- last-position lm_head + on-device decision
   bf16* logits = d_last_logits ? static_cast<bf16*>(d_last_logits) : e->logits;
-  if (gemm_store16(FMT_BF16, 1, e->lm_head, c.vocab_size, e->xn_last, n_seqs, H, logits, c.vocab_size, nullptr, ACT_NONE,
-                   swap_bn(n_seqs), st))
+  if (gemm_ws_store16(FMT_BF16, e->lm_head, c.vocab_size, e->xn_last, n_seqs, H, logits, c.vocab_size, nullptr, ACT_NONE, st))
     return -1;
   DecisionOut* dec_out = d_decisions ? reinterpret_cast<DecisionOut*>(d_decisions) : e->decisions;
   decision_kernel<<<n_seqs, 1024, 0, st>>>(logits, c.vocab_size, interval_id, dec_out);
@@ -770,8 +774,8 @@ int vlo_last_step_hidden(vlo_engine* e, void* d_hidden, void* cuda_stream) {
 int vlo_last_step_logits(vlo_engine* e, void* d_logits, void* cuda_stream) {
   VLO_CHECK(e != nullptr && e->last_step_tokens > 0, "no decoder step has run");
   const vlo_config& c = e->cfg;
-  return gemm_store16(FMT_BF16, 1, e->lm_head, c.vocab_size, e->xn, e->last_step_tokens, c.hidden_size, d_logits,
-                      c.vocab_size, nullptr, ACT_NONE, swap_bn(e->last_step_tokens), static_cast<cudaStream_t>(cuda_stream));
+  return gemm_ws_store16(FMT_BF16, e->lm_head, c.vocab_size, e->xn, e->last_step_tokens, c.hidden_size, d_logits,
+                         c.vocab_size, nullptr, ACT_NONE, static_cast<cudaStream_t>(cuda_stream));
 }
 
 }  // extern "C"

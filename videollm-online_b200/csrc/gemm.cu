@@ -2,6 +2,7 @@
 // resolved at run time, so the library loads on a box without libcuda), tile-shape
 // selection and kernel dispatch.
 #include "gemm.cuh"
+#include "gemm_ws.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -189,6 +190,88 @@ int gemm_launch(const GemmCall& c, cudaStream_t stream) {
 #undef VLO_GEMM_CASE
   return fail("gemm_launch: no kernel instance for fmt=" + std::to_string(c.fmt) + " bn=" +
               std::to_string(bn) + " swap=" + std::to_string(c.swap) + " epi=" + std::to_string(c.epi));
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent weight-streaming GEMM (gemm_ws.cuh)
+namespace {
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int FMT, int BN>
+int launch_ws(const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsArgs& a, cudaStream_t stream) {
+  auto kern = gemm_ws_kernel<FMT, BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmWsCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  if (prof_on()) {
+    const double out_b = a.mode == 0 ? 4.0 * a.rows_x * a.rows_w : 2.0 * a.rows_x * a.rows_w;
+    prof_begin(PROF_GEMM_STREAM, stream, 2.0 * a.k * (static_cast<double>(a.rows_w) + a.rows_x) + out_b);
+  }
+  kern<<<a.sk.G, kGemmThreads, GemmWsCfg<BN>::kSmemBytes, stream>>>(tw, tx, a);
+  prof_end(stream);
+  VLO_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+}
+}  // namespace
+
+int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_planes) {
+  const int tiles = (rows_w + kGemmBM - 1) / kGemmBM;
+  const int kb = k / kGemmBK;
+  sk->kb = kb;
+  sk->U = static_cast<long long>(tiles) * kb;
+  const long long cap = mode == 0 ? sk->U : tiles;
+  int G = n_ctas > 0 ? n_ctas : num_sms();
+  if (G > cap) G = static_cast<int>(cap);
+  sk->G = G;
+  int mp = 1;
+  if (mode == 0)
+    for (int t = 0; t < tiles; ++t) mp = std::max(mp, sk_planes(t, *sk));
+  if (max_planes) *max_planes = mp;
+  return 0;
+}
+
+int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream) {
+  VLO_CHECK(c.k > 0 && c.k % kGemmBK == 0, "K must be a positive multiple of 64");
+  VLO_CHECK(c.rows_w > 0 && c.rows_x > 0 && c.rows_x <= 128, "weight-streaming GEMM handles 1..128 token rows");
+  const int bn = c.rows_x <= 16 ? 16 : (c.rows_x <= 32 ? 32 : (c.rows_x <= 64 ? 64 : 128));
+  GemmWsArgs a{};
+  a.rows_w = c.rows_w;
+  a.rows_x = c.rows_x;
+  a.k = c.k;
+  a.tiles = (c.rows_w + kGemmBM - 1) / kGemmBM;
+  a.sk = c.sk;
+  a.mode = c.mode;
+  a.out = c.out;
+  a.ld_out = c.ld_out;
+  a.plane_stride = c.plane_stride;
+  a.bias = c.bias;
+  a.act = c.act;
+  CUtensorMap tw, tx;
+  if (get_tmap(c.w, c.rows_w, c.k, kGemmBM, c.fmt, &tw) != 0) return -1;
+  if (get_tmap(c.x, c.rows_x, c.k, bn, c.fmt, &tx) != 0) return -1;
+#define VLO_WS_CASE(F, N) \
+  if (c.fmt == F && bn == N) return launch_ws<F, N>(tw, tx, a, stream);
+  VLO_WS_CASE(FMT_BF16, 16)
+  VLO_WS_CASE(FMT_BF16, 32)
+  VLO_WS_CASE(FMT_BF16, 64)
+  VLO_WS_CASE(FMT_BF16, 128)
+  VLO_WS_CASE(FMT_F16, 16)
+  VLO_WS_CASE(FMT_F16, 32)
+  VLO_WS_CASE(FMT_F16, 64)
+  VLO_WS_CASE(FMT_F16, 128)
+#undef VLO_WS_CASE
+  return fail("gemm_ws_launch: no kernel instance");
 }
 
 }  // namespace vlo

@@ -193,6 +193,8 @@ class Engine:
         n = len(stream_ids)
         T = int(sum(q_lens))
         embeds = embeds.contiguous()
+        if T > self.max_step_tokens:
+            return self._step_chunked(stream_ids, q_lens, embeds, prefix_ids, interval_id, want_logits)
         if embeds.dtype != torch.bfloat16 or embeds.device != self.device or embeds.numel() != T * self.cfg.hidden_size:
             raise VloError(f"step: embeds must be bf16 [{T},{self.cfg.hidden_size}] on {self.device}")
         sid = (C.c_int32 * n)(*stream_ids)
@@ -207,6 +209,47 @@ class Engine:
         check(self.lib.vlo_step_ids(self._h, n, sid, ql, _ptr(pid), _ptr(embeds), _ptr(logits), _ptr(self._dec_dev), iid,
                                     self._stream()), "vlo_step")
         return logits, self._dec_dev[:n]
+
+    def _step_chunked(self, stream_ids, q_lens, embeds, prefix_ids, interval_id, want_logits):
+        """Inputs longer than max_step_tokens (the first frame's system prompt, long queries): feed the KV-append
+        forward in pieces — chunked streaming is exactly one causal pass.  Each
+        sequence's logits / decision come from the sub-step that holds its last piece."""
+        n, cap, H = len(stream_ids), self.max_step_tokens, self.cfg.hidden_size
+        if prefix_ids is not None:  # materialise the gathered prefix rows once; the sub-steps then see plain embeddings
+            embeds = embeds.clone()
+            starts = [int(sum(q_lens[:i])) for i in range(n)]
+            pid = prefix_ids.to(self.device).view(-1)
+            rows = self.embed_tokens(pid.clamp(min=0))
+            for i, st in enumerate(starts):
+                if int(pid[i]) >= 0:
+                    embeds[st] = rows[i]
+        logits_out = torch.empty(n, self.cfg.vocab_size, dtype=torch.bfloat16, device=self.device) if want_logits else None
+        dec_out = torch.empty(n, DECISION_DTYPE_FIELDS, dtype=torch.int32, device=self.device)
+        off, done = 0, [0] * n
+        starts = [int(sum(q_lens[:i])) for i in range(n)]
+        while any(done[i] < q_lens[i] for i in range(n)):
+            sub_ids, sub_lens, sub_rows, room = [], [], [], cap
+            for i in range(n):
+                left = q_lens[i] - done[i]
+                if left <= 0 or room <= 0:
+                    continue
+                take = min(left, room)
+                sub_ids.append(i)
+                sub_lens.append(take)
+                sub_rows.append(embeds[starts[i] + done[i]: starts[i] + done[i] + take])
+                room -= take
+            lg, dc = self.step([stream_ids[i] for i in sub_ids], sub_lens, torch.cat(sub_rows, 0), interval_id=interval_id,
+                               want_logits=want_logits)
+            for j, i in enumerate(sub_ids):
+                done[i] += sub_lens[j]
+                if done[i] == q_lens[i]:
+                    dec_out[i].copy_(dc[j])
+                    if want_logits:
+                        logits_out[i].copy_(lg[j])
+        self._dec_dev[:n].copy_(dec_out)
+        if want_logits:
+            self._logits[:n].copy_(logits_out)
+        return (self._logits[:n] if want_logits else None), self._dec_dev[:n]
 
     def read_decisions(self, n: int) -> List[Decision]:
         """One small D2H copy + sync: the only host<->device sync of a frame step."""
