@@ -197,6 +197,24 @@ def test_state_machine_vs_reference_liveinfer(built, golden, tiny):
     assert li._n_calls == golden["sm_calls"]
 
 
+def test_long_prompt_is_chunked_exactly(built, tiny):
+    """inputs longer than max_step_tokens are fed in pieces; chunked streaming == one pass (Appendix C.1)"""
+    cfg, _, _ = tiny
+    model, _ = built
+    eng = model.engine
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(300, cfg.hidden_size, generator=g).to(torch.bfloat16).cuda()
+    a = eng.stream_open()
+    la, _ = eng.step([a], [300], x)
+    la = la[0].clone()
+    b = eng.stream_open()
+    for lo, hi in ((0, 128), (128, 256), (256, 300)):
+        lb, _ = eng.step([b], [hi - lo], x[lo:hi])
+    assert torch.equal(la, lb[0]) and eng.kv_len(a) == eng.kv_len(b) == 300
+    eng.stream_close(a)
+    eng.stream_close(b)
+
+
 def test_kv_truncate_and_reset(built, tiny):
     cfg, _, _ = tiny
     model, _ = built
@@ -226,8 +244,9 @@ def test_error_paths(built, tiny):
     with pytest.raises(VloError):
         eng.step([99], [1], torch.zeros(1, cfg.hidden_size, dtype=torch.bfloat16, device="cuda"))
     s = eng.stream_open()
-    with pytest.raises(VloError):  # exceeds max_step_tokens
-        eng.step([s], [129], torch.zeros(129, cfg.hidden_size, dtype=torch.bfloat16, device="cuda"))
+    with pytest.raises(VloError):  # exceeds the stream's KV capacity (1024)
+        eng.step([s], [1025], torch.zeros(1025, cfg.hidden_size, dtype=torch.bfloat16, device="cuda"))
+    eng.stream_reset(s)
     with pytest.raises(VloError):
         eng.vit_encode(torch.zeros(1, 3, 32, 32, dtype=torch.uint8))
     eng.stream_close(s)

@@ -82,7 +82,8 @@ struct vlo_engine {
   // ViT workspaces
   __half *patches = nullptr, *v_xn = nullptr, *v_qkv = nullptr, *v_attn = nullptr, *v_mlp = nullptr, *v_pa = nullptr,
          *v_resid = nullptr, *v_lnh = nullptr, *v_m1 = nullptr, *v_m2 = nullptr;
-  float *v_h = nullptr, *v_ln32 = nullptr, *tokens32 = nullptr;
+  float *v_h = nullptr, *v_ln32 = nullptr, *tokens32 = nullptr, *v_part = nullptr;
+  size_t v_part_elems = 0;
   bf16 *tokens16 = nullptr, *conn_mid = nullptr;
 };
 
@@ -270,6 +271,8 @@ int vlo_engine_create(const vlo_config* cfg, int device, vlo_engine** out) {
     if (dev_alloc_t(e, &e->patches, rows * e->patch_k)) return -1;
     if (dev_alloc_t(e, &e->v_h, rows * C)) return -1;
     if (dev_alloc_t(e, &e->v_ln32, rows * C)) return -1;
+    e->v_part_elems = static_cast<size_t>(8) * rows * C;
+    if (dev_alloc_t(e, &e->v_part, e->v_part_elems)) return -1;
     if (dev_alloc_t(e, &e->v_xn, rows * C)) return -1;
     if (dev_alloc_t(e, &e->v_qkv, rows * 3 * C)) return -1;
     if (dev_alloc_t(e, &e->v_attn, rows * C)) return -1;
@@ -521,27 +524,58 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
   CUtensorMap tm_qkv;
   if (tmap_2d_sw128(e->v_qkv, rows, 3 * C, kVitBlk, FMT_F16, &tm_qkv)) return -1;
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // head_dim 64
-  auto resid_gemm = [&](const __half* a, const __half* w, const float* bias, int k) -> int {
+  // out_proj / fc2 have few output tiles (N = C): split K so ~all SMs stream, then fuse the split-K fix-up,
+  // the fp32 residual add and the NEXT LayerNorm into one row kernel.
+  const int bn_c = 64;
+  const int tiles_c = ((rows + 127) / 128) * ((C + bn_c - 1) / bn_c);
+  auto pick_splits = [&](int k) {
+    int s = std::max(1, (2 * kNumSMs) / std::max(1, tiles_c));
+    s = std::min(s, std::max(1, (k / kGemmBK) / 4));
+    return gemm_fix_splits(k, std::min(s, 8));
+  };
+  VLO_CHECK(static_cast<size_t>(8) * rows * C <= e->v_part_elems, "ViT split-K workspace too small");
+  auto partial_gemm = [&](const __half* a, const __half* w, int k, int* splits) -> int {
     GemmCall g{};
     g.fmt = FMT_F16;
     g.swap = 0;
-    g.epi = EPI_RESID32;
+    g.epi = EPI_PARTIAL;
     g.a = a;
     g.rows_a = rows;
     g.b = w;
     g.rows_b = C;
     g.k = k;
-    g.out = e->v_h;
+    g.out = e->v_part;
     g.ld_out = C;
-    g.bias = bias;
-    g.splits = 1;
-    g.bn = vit_bn(rows, C);
+    g.splits = pick_splits(k);
+    g.split_stride = static_cast<long long>(rows) * C;
+    g.bn = bn_c;
+    *splits = g.splits;
     return gemm_launch(g, st);
   };
+  auto fix_ln = [&](int splits, const float* bias, const float* lw, const float* lb, float* out32) -> int {
+    VitFixLnParams p{};
+    p.part = e->v_part;
+    p.n_splits = splits;
+    p.split_stride = static_cast<long long>(rows) * C;
+    p.bias = bias;
+    p.h = e->v_h;
+    p.ln_w = lw;
+    p.ln_b = lb;
+    p.out16 = e->v_xn;
+    p.out32 = out32;
+    p.C = C;
+    p.eps = c.vit_ln_eps;
+    vit_fix_ln_kernel<<<rows, 256, ln_smem, st>>>(p);
+    VLO_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+  };
+  layernorm_kernel<float><<<rows, 256, ln_smem, st>>>(e->v_h, e->vit[0].ln1_w, e->vit[0].ln1_b, e->v_xn, nullptr, C, c.vit_ln_eps);
+  VLO_LAUNCH_CHECK();
+  count_launch();
   for (int l = 0; l < c.vit_layers; ++l) {
     const VitLayer& v = e->vit[l];
-    layernorm_kernel<float><<<rows, 256, ln_smem, st>>>(e->v_h, v.ln1_w, v.ln1_b, e->v_xn, nullptr, C, c.vit_ln_eps);
-    VLO_LAUNCH_CHECK();
+    int S = 1;
     if (gemm_store16(FMT_F16, 0, e->v_xn, rows, v.qkv_w, 3 * C, C, e->v_qkv, 3 * C, v.qkv_b, ACT_NONE, vit_bn(rows, 3 * C), st))
       return -1;
     prof_begin(PROF_VIT_ATTN, st, 4.0 * rows * C * 2);
@@ -549,18 +583,19 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
         tm_qkv, e->v_attn, P, C, scale_log2);
     prof_end(st);
     VLO_LAUNCH_CHECK();
-    if (resid_gemm(e->v_attn, v.out_w, v.out_b, C)) return -1;
-    layernorm_kernel<float><<<rows, 256, ln_smem, st>>>(e->v_h, v.ln2_w, v.ln2_b, e->v_xn, nullptr, C, c.vit_ln_eps);
-    VLO_LAUNCH_CHECK();
+    count_launch();
+    if (partial_gemm(e->v_attn, v.out_w, C, &S)) return -1;
+    if (fix_ln(S, v.out_b, v.ln2_w, v.ln2_b, nullptr)) return -1;
     if (gemm_store16(FMT_F16, 0, e->v_xn, rows, v.fc1_w, M, C, e->v_mlp, M, v.fc1_b, ACT_GELU_TANH, vit_bn(rows, M), st))
       return -1;
-    if (resid_gemm(e->v_mlp, v.fc2_w, v.fc2_b, M)) return -1;
-    count_launch(3);
+    if (partial_gemm(e->v_mlp, v.fc2_w, M, &S)) return -1;
+    const bool last = (l == c.vit_layers - 1);
+    // the LayerNorm that follows fc2: next block's layer_norm1, or post_layernorm (fp16 copy feeds the MAP
+    // head, fp32 copy feeds the pool)
+    if (fix_ln(S, v.fc2_b, last ? e->post_ln_w : e->vit[l + 1].ln1_w, last ? e->post_ln_b : e->vit[l + 1].ln1_b,
+               last ? e->v_ln32 : nullptr))
+      return -1;
   }
-  // post-LN: fp16 copy feeds the MAP head, fp32 copy feeds the pool
-  layernorm_kernel<float><<<rows, 256, ln_smem, st>>>(e->v_h, e->post_ln_w, e->post_ln_b, e->v_xn, e->v_ln32, C, c.vit_ln_eps);
-  VLO_LAUNCH_CHECK();
-  count_launch();
   const int NT = e->n_frame_tokens;
   const int cls = c.frame_token_cls ? 1 : 0;
   if (c.pool_h * c.pool_w > 0) {

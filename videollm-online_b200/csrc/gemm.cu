@@ -185,6 +185,8 @@ int gemm_launch(const GemmCall& c, cudaStream_t stream) {
   VLO_GEMM_CASE(FMT_F16, 128, false, EPI_STORE16)
   VLO_GEMM_CASE(FMT_F16, 64, false, EPI_RESID32)
   VLO_GEMM_CASE(FMT_F16, 128, false, EPI_RESID32)
+  VLO_GEMM_CASE(FMT_F16, 64, false, EPI_PARTIAL)
+  VLO_GEMM_CASE(FMT_F16, 128, false, EPI_PARTIAL)
   VLO_GEMM_CASE(FMT_F16, 64, false, EPI_PATCH32)
   VLO_GEMM_CASE(FMT_F16, 128, false, EPI_PATCH32)
 #undef VLO_GEMM_CASE

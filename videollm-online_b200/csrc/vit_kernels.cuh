@@ -80,6 +80,63 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const InT* in, const flo
   }
 }
 
+// Split-K fix-up + fp32 residual add + LayerNorm in one pass over a token row:
+//   y    = fp16(sum_s part[s][r][:] + bias)      (the out_proj / fc2 Linear output under fp16 autocast)
+//   h[r] += y                                     (fp32 residual stream, HF:...siglip.py:353,360)
+//   out  = LayerNorm(h[r])                        (the next layer_norm1 / layer_norm2 / post_layernorm)
+struct VitFixLnParams {
+  const float* part;  // [n_splits][rows][C]
+  int n_splits;
+  long long split_stride;
+  const float* bias;
+  float* h;
+  const float* ln_w;
+  const float* ln_b;
+  __half* out16;
+  float* out32;
+  int C;
+  float eps;
+};
+__global__ void __launch_bounds__(256) vit_fix_ln_kernel(const VitFixLnParams p) {
+  extern __shared__ float row[];
+  __shared__ float red[32];
+  const size_t r = blockIdx.x;
+  const int C = p.C;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    float y = 0.f;
+    for (int k = 0; k < p.n_splits; ++k) y += p.part[k * p.split_stride + r * C + i];
+    const float v = p.h[r * C + i] + fp16_round(y + p.bias[i]);
+    p.h[r * C + i] = v;
+    row[i] = v;
+    s += v;
+  }
+  s = warp_sum(s);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < nw; ++i) tot += red[i];
+  const float mean = tot / C;
+  __syncthreads();
+  float q = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float d = row[i] - mean;
+    q += d * d;
+  }
+  q = warp_sum(q);
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  float var = 0.f;
+  for (int i = 0; i < nw; ++i) var += red[i];
+  const float rstd = rsqrtf(var / C + p.eps);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float y = (row[i] - mean) * rstd * p.ln_w[i] + p.ln_b[i];
+    if (p.out16) p.out16[r * C + i] = __float2half_rn(y);
+    if (p.out32) p.out32[r * C + i] = y;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // ViT self-attention (K5): non-causal softmax(Q K^T / sqrt(64)) V, fp16, head_dim 64.
 // qkv: [B*N, 3C] fp16 (q | k | v column blocks, head h at column h*64 inside each).
