@@ -310,6 +310,11 @@ struct AttnMergeParams {
 };
 
 __global__ void __launch_bounds__(128) attn_merge_kernel(const AttnMergeParams p) {
+  // one block per (head, token): thread d owns one output dim.  The (max, sum) pairs of all splits are
+  // fetched in one parallel round into shared memory, turned into weights once, and the weighted sum of
+  // the partial rows then runs as independent (pipelined) loads.
+  __shared__ float s_m[160], s_w[160];
+  __shared__ float s_den;
   const int head = blockIdx.x, tok = blockIdx.y, d = threadIdx.x;
   const AttnItem it = p.items[p.tok_item[tok]];
   const int G = p.n_heads / p.n_kv_heads;
@@ -317,21 +322,39 @@ __global__ void __launch_bounds__(128) attn_merge_kernel(const AttnMergeParams p
   const int rows = it.q_count * G;
   const int r = (tok - it.q_tok0) * G + g;
   const float c = p.scale_log2;
+  const size_t slot0 = static_cast<size_t>(it.ws_slot0) + static_cast<size_t>(kvh) * it.n_splits * rows + r;
+  const int ns = it.n_splits;  // <= 148
+  float l_mine = 0.f;
+  for (int s = d; s < ns; s += 128) {
+    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + (slot0 + static_cast<size_t>(s) * rows) * 2);
+    s_m[s] = ml.x;
+    l_mine = ml.y;  // at most two splits per thread (ns <= 148 < 256); keep the second separately below
+    s_w[s] = ml.y;
+  }
+  __syncthreads();
   float mx = -INFINITY;
-  for (int s = 0; s < it.n_splits; ++s) {
-    const size_t slot = static_cast<size_t>(it.ws_slot0) + (static_cast<size_t>(kvh) * it.n_splits + s) * rows + r;
-    mx = fmaxf(mx, p.ws_ml[slot * 2]);
+  for (int s = 0; s < ns; ++s) mx = fmaxf(mx, s_m[s]);
+  __syncthreads();
+  for (int s = d; s < ns; s += 128) {
+    const float m = s_m[s];
+    const float w = (m == -INFINITY) ? 0.f : exp2f((m - mx) * c);
+    s_m[s] = w;            // weight
+    s_w[s] = s_w[s] * w;   // weighted row sum
   }
-  float acc = 0.f, den = 0.f;
-  for (int s = 0; s < it.n_splits; ++s) {
-    const size_t slot = static_cast<size_t>(it.ws_slot0) + (static_cast<size_t>(kvh) * it.n_splits + s) * rows + r;
-    const float m = p.ws_ml[slot * 2];
-    if (m == -INFINITY) continue;
-    const float w = exp2f((m - mx) * c);
-    den += p.ws_ml[slot * 2 + 1] * w;
-    acc += p.ws_o[slot * kAttnHD + d] * w;
+  __syncthreads();
+  if (d == 0) {
+    float den = 0.f;
+    for (int s = 0; s < ns; ++s) den += s_w[s];
+    s_den = den;
   }
-  p.out[(static_cast<size_t>(tok) * p.n_heads + head) * kAttnHD + d] = __float2bfloat16_rn(acc / den);
+  float acc = 0.f;
+  const float* o = p.ws_o + slot0 * kAttnHD + d;
+  const size_t stride = static_cast<size_t>(rows) * kAttnHD;
+#pragma unroll 4
+  for (int s = 0; s < ns; ++s) acc += o[s * stride] * s_m[s];
+  __syncthreads();
+  (void)l_mine;
+  p.out[(static_cast<size_t>(tok) * p.n_heads + head) * kAttnHD + d] = __float2bfloat16_rn(acc / s_den);
 }
 
 }  // namespace vlo
