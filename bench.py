@@ -228,14 +228,14 @@ def run_engine_arm(args):
     S = cfg.frame_resolution
     frames_host = torch.randint(0, 256, (n_frames, 3, S, S), dtype=torch.uint8, generator=g).pin_memory()
     frames_dev = frames_host.to(dev)
-    prefix = torch.tensor([cfg.frame_token_interval_id], dtype=torch.int64, device=dev)
+    prefix = torch.tensor([cfg.frame_token_interval_id] + [-1] * 10, dtype=torch.int64, device=dev)
     packed = torch.zeros(11, cfg.hidden_size, dtype=torch.bfloat16, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def frame_step_resident(i):           # inputs already in HBM, no host sync
         fe = eng.vit_encode(frames_dev[i:i + 1])
         packed[1:] = fe
-        eng.step([sid], [11], packed, prefix_ids=prefix, want_logits=True)
+        eng.step([sid], [11], packed, row_ids=prefix, want_logits=True)
 
     fbuf = torch.empty(1, 3, S, S, dtype=torch.uint8, device=dev)
 
@@ -243,7 +243,7 @@ def run_engine_arm(args):
         fbuf.copy_(frames_host[i:i + 1], non_blocking=True)
         fe = model.visual_embed(fbuf)
         packed[1:] = fe
-        eng.step([sid], [11], packed, prefix_ids=prefix, want_logits=True)
+        eng.step([sid], [11], packed, row_ids=prefix, want_logits=True)
         return eng.read_decisions(1)[0]
 
     def barrier():

@@ -126,11 +126,12 @@ int vlo_embed_tokens(vlo_engine* e, const int64_t* d_ids, int n, void* d_out, vo
  * Appends q_lens[i] tokens to stream i's KV cache. */
 int vlo_step(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const int32_t* h_q_lens, const void* d_embeds,
              void* d_last_logits, vlo_decision* d_decisions, int interval_id, void* cuda_stream);
-/* Same, but the first token row of every sequence is gathered from the embedding table by id
- * (d_prefix_ids[n_seqs], device int64; id < 0 = "row already present in d_embeds") — the steady-state
- * frame step [interval-token, 10 frame embeds] without a separate embedding launch. */
+/* Same, with token rows gathered on the device: d_row_ids[sum(q_lens)] (device int64), one entry per packed row;
+ * id >= 0 = "this row is the embedding of token id" (gathered from the table, clamped to vocab-1),
+ * id <  0 = "row already present in d_embeds" (a frame embedding).  The steady-state frame step is
+ * [interval id, -1 x 10]; an AR step is [last id]; no separate embedding launch or torch.cat. */
 int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const int32_t* h_q_lens,
-                 const int64_t* d_prefix_ids, const void* d_embeds, void* d_last_logits, vlo_decision* d_decisions,
+                 const int64_t* d_row_ids, const void* d_embeds, void* d_last_logits, vlo_decision* d_decisions,
                  int interval_id, void* cuda_stream);
 /* all-position logits for the last vlo_step's tokens (the reference's logits_to_keep=0 behaviour,
  * HF:models/llama/modeling_llama.py:485-487); d_logits bf16 [sum(q_lens), vocab]. Test/compat path. */

@@ -250,3 +250,60 @@ def test_error_paths(built, tiny):
     with pytest.raises(VloError):
         eng.vit_encode(torch.zeros(1, 3, 32, 32, dtype=torch.uint8))
     eng.stream_close(s)
+
+
+def test_multistream_scheduler_equals_independent_liveinfer(built, golden, tiny):
+    """configs 3/5: S concurrent streams batched per tick behave exactly like S separate LiveInfer sessions
+    (same frame decisions, response ids, KV accounting), with streams in different phases
+    (frame step / response prompt / AR token) sharing one ragged step."""
+    from videollm_online_b200.config import LiveArguments, SYSTEM_PROMPT
+    from videollm_online_b200.inference import LiveInfer
+    from videollm_online_b200.multistream import StreamScheduler
+    cfg, _, _ = tiny
+    model, tok = built
+    I, E, END = cfg.frame_token_interval_id, cfg.eos_token_id, cfg.stream_end_id
+    A, B = 300, 301
+    scripts = [  # per-stream call index -> forced token
+        {0: I, 1: END, 2: A, 3: B, 4: E, 5: I, 6: I},
+        {0: END, 1: E, 2: I, 3: END, 4: A, 5: E, 6: I},
+        {0: I, 1: I, 2: I, 3: END, 4: A, 5: A, 6: B, 7: E},
+    ]
+
+    def force(dec, t):
+        if t is not None:
+            dec.argmax_id = dec.argmax_prob_id = t
+            dec.p_interval = 1.0 if t == I else 0.0
+            if t != I:
+                dec.argmax_excl_id = t
+        return dec
+
+    videos = [golden["sm_video"][i:i + 5] for i in range(3)]
+    ref_events, ref_kv = [], []
+    for s in range(3):
+        li = LiveInfer(LiveArguments(frame_fps=2, system_prompt=SYSTEM_PROMPT), model=model, tokenizer=tok)
+        li.decision_hook = lambda d, n, s=s: force(d, scripts[s].get(n))
+        li.load_video(videos[s])
+        ev = []
+        for i in range(5):
+            li.input_video_stream(i / 2)
+            q, r = li()
+            ev.append((int(li.last_ids.reshape(-1)[-1]), li.past_key_values.get_seq_length(), r))
+        ref_events.append(ev)
+        ref_kv.append(li.past_key_values.get_seq_length())
+        model.engine.stream_close(li._kv.stream_id)
+
+    sched = StreamScheduler(model, tok, 3, frame_fps=2, system_prompt=SYSTEM_PROMPT)
+    sched.decision_hook = lambda s, d, n: force(d, scripts[s].get(n))
+    for s, sess in enumerate(sched.sessions):
+        sess.load_video(videos[s])
+    for i in range(5):
+        for sess in sched.sessions:
+            sess.input_video_stream(i / 2)
+        sched.run_until_idle()
+    for s, sess in enumerate(sched.sessions):
+        assert model.engine.kv_len(sess.stream_id) == ref_kv[s]
+        got = [o[2] for o in sess.outputs]
+        want = [e[2] for e in ref_events[s] if e[2] is not None]
+        assert got == want, (s, got, want)
+        model.engine.stream_close(sess.stream_id)
+    assert sched.frames_done == 15

@@ -132,9 +132,9 @@ int attn_run(const AttnPlan& plan, const void* d_q, const void* d_k, const void*
   p.n_kv_heads = n_kv_heads;
   p.scale_log2 = scale_log2;
   prof_begin(PROF_ATTN, stream, plan.algo_bytes);
-  attn_kvappend_kernel<<<dim3(plan.max_splits, n_kv_heads, plan.n_items), kAttnThreads, kAttnSmemBytes, stream>>>(tk, tv, p);
+  VLO_CUDA(launch_pdl(attn_kvappend_kernel, dim3(plan.max_splits, n_kv_heads, plan.n_items), dim3(kAttnThreads),
+                      kAttnSmemBytes, stream, tk, tv, p));
   prof_end(stream);
-  VLO_LAUNCH_CHECK();
   AttnMergeParams mp{};
   mp.ws_o = plan.ws_o;
   mp.ws_ml = plan.ws_ml;
@@ -145,9 +145,8 @@ int attn_run(const AttnPlan& plan, const void* d_q, const void* d_k, const void*
   mp.n_kv_heads = n_kv_heads;
   mp.scale_log2 = scale_log2;
   prof_begin(PROF_ATTN_MERGE, stream, 0.0);
-  attn_merge_kernel<<<dim3(n_heads, plan.total_tokens), 128, 0, stream>>>(mp);
+  VLO_CUDA(launch_pdl(attn_merge_kernel, dim3(n_heads, plan.total_tokens), dim3(128), 0, stream, mp));
   prof_end(stream);
-  VLO_LAUNCH_CHECK();
   count_launch(2);
   return 0;
 }

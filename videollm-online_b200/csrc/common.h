@@ -35,6 +35,24 @@ int fail(const std::string& msg);  // set_error + return -1
                          __FILE__ + ":" + std::to_string(__LINE__));                    \
   } while (0)
 
+// Kernel launch with the PDL attribute (see ptx.cuh: pdl_wait / pdl_trigger).  Every kernel launched through
+// this helper calls pdl_wait() before its first dependent global access.  VLO_NO_PDL=1 disables the attribute.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Launch counter (the bench reports how many of OUR kernels ran in the timed region).
 void count_launch(int n = 1);
 long long launch_count();

@@ -47,41 +47,60 @@ struct ResidNormParams {
   float eps;
 };
 
-__global__ void __launch_bounds__(256) resid_rmsnorm_kernel(const ResidNormParams p) {
+constexpr int kFixMaxPlanes = 8;  // stream-K never needs more (engine checks)
+
+__global__ void __launch_bounds__(1024) resid_rmsnorm_kernel(const ResidNormParams p) {
+  // one CTA per token row, 4 contiguous elements per thread per sweep; the plane loads of a sweep are
+  // independent (predicated, fully unrolled) so they are all in flight together.
   extern __shared__ float row[];  // H floats
   __shared__ float red[32];
   const int t = blockIdx.x;
   __nv_bfloat16* h = p.h + static_cast<size_t>(t) * p.H;
+  pdl_wait();
+  pdl_trigger();
   float ss = 0.f;
-  for (int i = threadIdx.x * 2; i < p.H; i += blockDim.x * 2) {
-    float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(h + i));
+  for (int i = threadIdx.x * 4; i < p.H; i += blockDim.x * 4) {
+    const uint2 hraw = *reinterpret_cast<const uint2*>(h + i);
+    float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw.x));
+    float2 v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw.y));
     if (p.n_splits != 0) {
-      float y0 = 0.f, y1 = 0.f;
-      const float* pp = p.part + static_cast<size_t>(t) * p.H + i;
       const int ns = p.n_splits > 0 ? p.n_splits : sk_planes(i >> 7, p.sk);
-      for (int s = 0; s < ns; ++s) {
-        const float2 a = *reinterpret_cast<const float2*>(pp + s * p.split_stride);
-        y0 += a.x;
-        y1 += a.y;
+      const float* pp = p.part + static_cast<size_t>(t) * p.H + i;
+      float4 a[kFixMaxPlanes];
+#pragma unroll
+      for (int s = 0; s < kFixMaxPlanes; ++s)
+        a[s] = (s < ns) ? *reinterpret_cast<const float4*>(pp + s * p.split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+#pragma unroll
+      for (int s = 0; s < kFixMaxPlanes; ++s) {  // plane order: deterministic
+        y0 += a[s].x; y1 += a[s].y; y2 += a[s].z; y3 += a[s].w;
       }
-      v.x = bf16_round(v.x + bf16_round(y0));
-      v.y = bf16_round(v.y + bf16_round(y1));
-      *reinterpret_cast<__nv_bfloat162*>(h + i) = __floats2bfloat162_rn(v.x, v.y);
+      v01.x = bf16_round(v01.x + bf16_round(y0));
+      v01.y = bf16_round(v01.y + bf16_round(y1));
+      v23.x = bf16_round(v23.x + bf16_round(y2));
+      v23.y = bf16_round(v23.y + bf16_round(y3));
+      uint2 o;
+      *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v01.x, v01.y);
+      *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v23.x, v23.y);
+      *reinterpret_cast<uint2*>(h + i) = o;
     }
-    row[i] = v.x;
-    row[i + 1] = v.y;
-    ss += v.x * v.x + v.y * v.y;
+    row[i] = v01.x; row[i + 1] = v01.y; row[i + 2] = v23.x; row[i + 3] = v23.y;
+    ss += v01.x * v01.x + v01.y * v01.y + v23.x * v23.x + v23.y * v23.y;
   }
   const float tot = block_sum(ss, red);
   const float rstd = rsqrtf(tot / static_cast<float>(p.H) + p.eps);
   const int li = p.last_index ? p.last_index[t] : -1;
-  for (int i = threadIdx.x * 2; i < p.H; i += blockDim.x * 2) {
-    const float2 w = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.w + i));
-    const float a = bf16_round(w.x * bf16_round(row[i] * rstd));
-    const float b = bf16_round(w.y * bf16_round(row[i + 1] * rstd));
-    const __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
-    if (p.xn) *reinterpret_cast<__nv_bfloat162*>(p.xn + static_cast<size_t>(t) * p.H + i) = o;
-    if (li >= 0) *reinterpret_cast<__nv_bfloat162*>(p.xn_last + static_cast<size_t>(li) * p.H + i) = o;
+  for (int i = threadIdx.x * 4; i < p.H; i += blockDim.x * 4) {
+    const uint2 wraw = *reinterpret_cast<const uint2*>(p.w + i);
+    const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wraw.x));
+    const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wraw.y));
+    uint2 o;
+    *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(bf16_round(w01.x * bf16_round(row[i] * rstd)),
+                                                                     bf16_round(w01.y * bf16_round(row[i + 1] * rstd)));
+    *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(bf16_round(w23.x * bf16_round(row[i + 2] * rstd)),
+                                                                     bf16_round(w23.y * bf16_round(row[i + 3] * rstd)));
+    if (p.xn) *reinterpret_cast<uint2*>(p.xn + static_cast<size_t>(t) * p.H + i) = o;
+    if (li >= 0) *reinterpret_cast<uint2*>(p.xn_last + static_cast<size_t>(li) * p.H + i) = o;
   }
 }
 
@@ -111,6 +130,8 @@ struct QkvRopeParams {
 
 __global__ void __launch_bounds__(64) qkv_rope_append_kernel(const QkvRopeParams p) {
   const int t = blockIdx.x, hh = blockIdx.y, d = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   const int width = (p.n_heads + 2 * p.n_kv_heads) * 128;
   const float* pp = p.part + static_cast<size_t>(t) * width + hh * 128 + d;
   float x1 = 0.f, x2 = 0.f;
@@ -154,27 +175,39 @@ struct SwigluParams {
   int T, I;
 };
 __global__ void __launch_bounds__(256) swiglu_kernel(const SwigluParams p) {
-  const long long n2 = static_cast<long long>(p.T) * p.I / 2;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n2;
+  pdl_wait();
+  pdl_trigger();
+  const long long n4 = static_cast<long long>(p.T) * p.I / 4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n4;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long e = idx * 2;
+    const long long e = idx * 4;
     const int t = static_cast<int>(e / p.I), i = static_cast<int>(e % p.I);
     const float* pg = p.part + static_cast<size_t>(t) * 2 * p.I + i;
-    float g0 = 0.f, g1 = 0.f, u0 = 0.f, u1 = 0.f;
     const int ng = p.n_splits > 0 ? p.n_splits : sk_planes(i >> 7, p.sk);
     const int nu = p.n_splits > 0 ? p.n_splits : sk_planes((p.I + i) >> 7, p.sk);
-    for (int s = 0; s < ng; ++s) {
-      const float2 g = *reinterpret_cast<const float2*>(pg + s * p.split_stride);
-      g0 += g.x; g1 += g.y;
+    float4 ga[kFixMaxPlanes], ua[kFixMaxPlanes];
+#pragma unroll
+    for (int s = 0; s < kFixMaxPlanes; ++s) {
+      ga[s] = (s < ng) ? *reinterpret_cast<const float4*>(pg + s * p.split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ua[s] = (s < nu) ? *reinterpret_cast<const float4*>(pg + s * p.split_stride + p.I) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int s = 0; s < nu; ++s) {
-      const float2 u = *reinterpret_cast<const float2*>(pg + s * p.split_stride + p.I);
-      u0 += u.x; u1 += u.y;
+    float g[4] = {0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < kFixMaxPlanes; ++s) {
+      g[0] += ga[s].x; g[1] += ga[s].y; g[2] += ga[s].z; g[3] += ga[s].w;
+      u[0] += ua[s].x; u[1] += ua[s].y; u[2] += ua[s].z; u[3] += ua[s].w;
     }
-    g0 = bf16_round(g0); g1 = bf16_round(g1); u0 = bf16_round(u0); u1 = bf16_round(u1);
-    const float a0 = bf16_round(g0 / (1.0f + expf(-g0)));
-    const float a1 = bf16_round(g1 / (1.0f + expf(-g1)));
-    *reinterpret_cast<__nv_bfloat162*>(p.act + e) = __floats2bfloat162_rn(a0 * u0, a1 * u1);
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = bf16_round(g[k]), uk = bf16_round(u[k]);
+      const float a = bf16_round(gk / (1.0f + expf(-gk)));
+      o[k] = a * uk;
+    }
+    uint2 w;
+    *reinterpret_cast<__nv_bfloat162*>(&w.x) = __floats2bfloat162_rn(o[0], o[1]);
+    *reinterpret_cast<__nv_bfloat162*>(&w.y) = __floats2bfloat162_rn(o[2], o[3]);
+    *reinterpret_cast<uint2*>(p.act + e) = w;
   }
 }
 
@@ -222,82 +255,101 @@ struct DecisionOut {  // == vlo_decision
 
 __global__ void __launch_bounds__(1024) decision_kernel(const __nv_bfloat16* logits, int vocab, int interval_id,
                                                         DecisionOut* out) {
-  __shared__ float s_val[32];
-  __shared__ int s_idx[32];
-  __shared__ float s_val2[32];
-  __shared__ float s_bcast[2];
+  // Two vectorised sweeps over the row (16-byte loads, 8 logits each):
+  //   A: first-index max, second max and the online sum of exponentials;
+  //   B: argmax of the bf16-rounded probabilities with / without the interval id.
+  __shared__ float s_m1[32], s_m2[32], s_se[32], s_pa[32], s_pe[32];
+  __shared__ int s_i1[32], s_ia[32], s_ie[32];
+  __shared__ float s_gmax, s_gmax2, s_sum;
+  __shared__ int s_gidx;
+  pdl_wait();
+  pdl_trigger();
   const __nv_bfloat16* x = logits + static_cast<size_t>(blockIdx.x) * vocab;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int nvec = vocab / 8;  // rows are 16-byte aligned (vocab % 8 == 0 checked by the engine); tail handled below
 
-  // pass 1: max (first index), second max
-  float m1 = -INFINITY, m2 = -INFINITY;
+  // ---- sweep A
+  float m1 = -INFINITY, m2 = -INFINITY, se = 0.f;
   int i1 = 0x7fffffff;
-  for (int i = tid; i < vocab; i += blockDim.x) {
-    const float v = __bfloat162float(x[i]);
-    if (v > m1) { m2 = m1; m1 = v; i1 = i; }
-    else if (v > m2) m2 = v;  // a tie with m1 at a later index lands here -> margin 0
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    const float om1 = __shfl_xor_sync(0xffffffffu, m1, o);
-    const float om2 = __shfl_xor_sync(0xffffffffu, m2, o);
-    const int oi1 = __shfl_xor_sync(0xffffffffu, i1, o);
-    if (om1 > m1 || (om1 == m1 && oi1 < i1)) { m2 = fmaxf(m1, om2); m1 = om1; i1 = oi1; }
-    else m2 = fmaxf(m2, om1);
-  }
-  if (lane == 0) { s_val[warp] = m1; s_idx[warp] = i1; s_val2[warp] = m2; }
-  __syncthreads();
-  if (warp == 0) {
-    m1 = lane < nw ? s_val[lane] : -INFINITY;
-    i1 = lane < nw ? s_idx[lane] : 0x7fffffff;
-    m2 = lane < nw ? s_val2[lane] : -INFINITY;
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om1 = __shfl_xor_sync(0xffffffffu, m1, o);
-      const float om2 = __shfl_xor_sync(0xffffffffu, m2, o);
-      const int oi1 = __shfl_xor_sync(0xffffffffu, i1, o);
-      if (om1 > m1 || (om1 == m1 && oi1 < i1)) { m2 = fmaxf(m1, om2); m1 = om1; i1 = oi1; }
-      else m2 = fmaxf(m2, om1);
+  auto take = [&](float v, int idx) {
+    if (v > m1) {
+      se = se * __expf(m1 - v) + 1.f;  // m1 = -inf on the first element: se = 0 * 0 + 1
+      m2 = m1; m1 = v; i1 = idx;
+    } else {
+      se += __expf(v - m1);
+      if (v > m2) m2 = v;
     }
-    if (lane == 0) { s_val[0] = m1; s_idx[0] = i1; s_val2[0] = m2; }
+  };
+  for (int vi = tid; vi < nvec; vi += blockDim.x) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(vi) * 8);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+      take(f.x, vi * 8 + 2 * k);
+      take(f.y, vi * 8 + 2 * k + 1);
+    }
   }
-  __syncthreads();
-  const float gmax = s_val[0];
-  const int gidx = s_idx[0];
-  const float gmax2 = s_val2[0];
-  __syncthreads();
-
-  // pass 2: sum of exp
-  float se = 0.f;
-  for (int i = tid; i < vocab; i += blockDim.x) se += expf(__bfloat162float(x[i]) - gmax);
-  se = warp_sum(se);
-  if (lane == 0) s_val[warp] = se;
+  for (int idx = nvec * 8 + tid; idx < vocab; idx += blockDim.x) take(__bfloat162float(x[idx]), idx);
+  auto merge = [&](float om1, int oi1, float om2, float ose) {
+    if (om1 > m1 || (om1 == m1 && oi1 < i1)) {
+      se = ose + se * __expf(m1 - om1);
+      m2 = fmaxf(m1, om2); m1 = om1; i1 = oi1;
+    } else if (oi1 != 0x7fffffff) {
+      se += ose * __expf(om1 - m1);
+      m2 = fmaxf(m2, om1);
+    }
+  };
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om1 = __shfl_xor_sync(0xffffffffu, m1, o), om2 = __shfl_xor_sync(0xffffffffu, m2, o);
+    const float ose = __shfl_xor_sync(0xffffffffu, se, o);
+    const int oi1 = __shfl_xor_sync(0xffffffffu, i1, o);
+    merge(om1, oi1, om2, ose);
+  }
+  if (lane == 0) { s_m1[warp] = m1; s_i1[warp] = i1; s_m2[warp] = m2; s_se[warp] = se; }
   __syncthreads();
   if (warp == 0) {
-    float t = lane < nw ? s_val[lane] : 0.f;
-    t = warp_sum(t);
-    if (lane == 0) s_bcast[0] = t;
+    m1 = lane < nw ? s_m1[lane] : -INFINITY;
+    i1 = lane < nw ? s_i1[lane] : 0x7fffffff;
+    m2 = lane < nw ? s_m2[lane] : -INFINITY;
+    se = lane < nw ? s_se[lane] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om1 = __shfl_xor_sync(0xffffffffu, m1, o), om2 = __shfl_xor_sync(0xffffffffu, m2, o);
+      const float ose = __shfl_xor_sync(0xffffffffu, se, o);
+      const int oi1 = __shfl_xor_sync(0xffffffffu, i1, o);
+      merge(om1, oi1, om2, ose);
+    }
+    if (lane == 0) { s_gmax = m1; s_gidx = i1; s_gmax2 = m2; s_sum = se; }
   }
   __syncthreads();
-  const float sum = s_bcast[0];
-  __syncthreads();
+  const float gmax = s_gmax, sum = s_sum;
 
-  // pass 3: argmax over the bf16-rounded probabilities (what the reference's
-  // next_score.argmax sees), with and without the interval id; first index wins ties.
+  // ---- sweep B: what `next_score.argmax` sees (demo/inference.py:76-79); first index wins ties
   float pa = -1.f, pe = -1.f;
   int ia = 0x7fffffff, ie = 0x7fffffff;
-  for (int i = tid; i < vocab; i += blockDim.x) {
-    const float pr = bf16_round(expf(__bfloat162float(x[i]) - gmax) / sum);
-    if (pr > pa) { pa = pr; ia = i; }
-    const float pz = (i == interval_id) ? 0.f : pr;  // zero_() then argmax (demo/inference.py:77-79)
-    if (pz > pe) { pe = pz; ie = i; }
+  auto prob = [&](float v, int idx) {
+    const float pr = bf16_round(__expf(v - gmax) / sum);
+    if (pr > pa) { pa = pr; ia = idx; }
+    const float pz = (idx == interval_id) ? 0.f : pr;  // zero_() then argmax
+    if (pz > pe) { pe = pz; ie = idx; }
+  };
+  for (int vi = tid; vi < nvec; vi += blockDim.x) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(vi) * 8);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+      prob(f.x, vi * 8 + 2 * k);
+      prob(f.y, vi * 8 + 2 * k + 1);
+    }
   }
+  for (int idx = nvec * 8 + tid; idx < vocab; idx += blockDim.x) prob(__bfloat162float(x[idx]), idx);
   for (int o = 16; o > 0; o >>= 1) {
     const float opa = __shfl_xor_sync(0xffffffffu, pa, o), ope = __shfl_xor_sync(0xffffffffu, pe, o);
     const int oia = __shfl_xor_sync(0xffffffffu, ia, o), oie = __shfl_xor_sync(0xffffffffu, ie, o);
     if (opa > pa || (opa == pa && oia < ia)) { pa = opa; ia = oia; }
     if (ope > pe || (ope == pe && oie < ie)) { pe = ope; ie = oie; }
   }
-  __shared__ float s_pa[32], s_pe[32];
-  __shared__ int s_ia[32], s_ie[32];
   if (lane == 0) { s_pa[warp] = pa; s_ia[warp] = ia; s_pe[warp] = pe; s_ie[warp] = ie; }
   __syncthreads();
   if (warp == 0) {
@@ -311,13 +363,13 @@ __global__ void __launch_bounds__(1024) decision_kernel(const __nv_bfloat16* log
     }
     if (lane == 0) {
       DecisionOut d;
-      d.argmax_id = gidx;
+      d.argmax_id = s_gidx;
       d.argmax_excl_id = ie;
       d.p_interval = (interval_id >= 0 && interval_id < vocab)
-                         ? bf16_round(expf(__bfloat162float(x[interval_id]) - gmax) / sum)
+                         ? bf16_round(__expf(__bfloat162float(x[interval_id]) - gmax) / sum)
                          : 0.f;
       d.max_logit = gmax;
-      d.top2_margin = gmax - gmax2;
+      d.top2_margin = gmax - s_gmax2;
       d.lse = gmax + logf(sum);
       d.argmax_prob_id = ia;
       d.reserved1 = 0;

@@ -120,6 +120,7 @@ int gemm_partial(vlo_engine* e, const bf16* w, int n_out, const bf16* x, int T, 
   int planes = 1;
   gemm_ws_plan(n_out, k, 0, 0, sk, &planes);
   VLO_CHECK(static_cast<size_t>(planes) * T * n_out <= e->part_elems, "stream-K workspace too small");
+  VLO_CHECK(planes <= kFixMaxPlanes, "stream-K produced more partial planes than the fix-up kernels unroll");
   GemmWsCall c{};
   c.fmt = FMT_BF16;
   c.mode = 0;
@@ -175,9 +176,16 @@ int gemm_store16(int fmt, int swap, const void* a, int rows_a, const void* b, in
   return gemm_launch(c, st);
 }
 
+// N-tile width for the ViT trunk GEMMs: prefer a single wave of CTAs (one CTA per SM); two waves cost 2x.
 int vit_bn(int rows, int n_out) {
-  const int tiles128 = ((rows + 127) / 128) * ((n_out + 127) / 128);
-  return tiles128 >= kNumSMs ? 128 : 64;
+  const int mt = (rows + 127) / 128;
+  const int t64 = mt * ((n_out + 63) / 64), t128 = mt * ((n_out + 127) / 128);
+  if (t64 <= kNumSMs) return 64;     // everything fits in one wave even with the narrow tile
+  if (t128 <= kNumSMs) return 128;   // one wave with the wide tile
+  // multi-wave: wide tiles (better operand reuse) unless the narrow ones waste much less of the last wave
+  const double e64 = static_cast<double>(t64) / (((t64 + kNumSMs - 1) / kNumSMs) * kNumSMs);
+  const double e128 = static_cast<double>(t128) / (((t128 + kNumSMs - 1) / kNumSMs) * kNumSMs);
+  return e64 > e128 + 0.15 ? 64 : 128;
 }
 
 // pinned staging slot, recycled behind a CUDA event
@@ -220,7 +228,8 @@ int vlo_engine_create(const vlo_config* cfg, int device, vlo_engine** out) {
   if (!vlo_device_supported(device)) return fail("device is not an sm_100 (Blackwell) GPU; there is no fallback path");
   const vlo_config& c = *cfg;
   VLO_CHECK(c.head_dim == 128, "decoder head_dim must be 128");
-  VLO_CHECK(c.hidden_size % 64 == 0 && c.intermediate_size % 64 == 0, "hidden/intermediate must be multiples of 64");
+  VLO_CHECK(c.vocab_size % 8 == 0, "vocab_size must be a multiple of 8 (16-byte aligned logits rows)");
+  VLO_CHECK(c.hidden_size % 128 == 0 && c.intermediate_size % 128 == 0, "hidden/intermediate must be multiples of 128");
   VLO_CHECK(c.num_heads % c.num_kv_heads == 0, "num_heads % num_kv_heads");
   VLO_CHECK(c.max_streams >= 1 && c.max_kv_tokens >= 64 && c.max_step_tokens >= 1, "capacities");
   VLO_CHECK(c.max_step_tokens <= 128, "max_step_tokens <= 128 (longer inputs are chunked by the host; chunked == one pass)");
@@ -647,7 +656,7 @@ int vlo_embed_tokens(vlo_engine* e, const int64_t* d_ids, int n, void* d_out, vo
 }
 
 int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const int32_t* h_q_lens,
-                 const int64_t* d_prefix_ids, const void* d_embeds, void* d_last_logits, vlo_decision* d_decisions,
+                 const int64_t* d_row_ids, const void* d_embeds, void* d_last_logits, vlo_decision* d_decisions,
                  int interval_id, void* cuda_stream) {
   VLO_CHECK(e != nullptr && e->finalized && e->has_decoder, "decoder weights not loaded");
   const vlo_config& c = e->cfg;
@@ -692,7 +701,6 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
   VLO_CUDA(cudaMemcpyAsync(e->meta_dev, hs, e->meta_bytes, cudaMemcpyHostToDevice, st));
   const int* d_tok_pos = reinterpret_cast<const int*>(e->meta_dev + o_pos);
   const int* d_last_index = reinterpret_cast<const int*>(e->meta_dev + o_last);
-  const int* d_first_rows = reinterpret_cast<const int*>(e->meta_dev + o_first);
   const long long* d_tok_kvrow = reinterpret_cast<const long long*>(e->meta_dev + o_row);
   AttnPlan plan{};
   if (attn_plan(&plan, e->attn_ws, hs + e->meta_bytes, seqs.data(), n_seqs, T, c.num_heads, c.num_kv_heads, c.head_dim, st))
@@ -701,9 +709,9 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
 
   // ---- residual stream <- packed input embeddings (+ prefix-token rows gathered by id)
   VLO_CUDA(cudaMemcpyAsync(e->h, d_embeds, static_cast<size_t>(T) * H * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
-  if (d_prefix_ids != nullptr) {
-    embed_rows_kernel<<<n_seqs, 256, 0, st>>>(reinterpret_cast<const long long*>(d_prefix_ids), d_first_rows, n_seqs,
-                                              e->embed, c.vocab_size, H, e->h);
+  if (d_row_ids != nullptr) {
+    embed_rows_kernel<<<T, 256, 0, st>>>(reinterpret_cast<const long long*>(d_row_ids), nullptr, T, e->embed, c.vocab_size,
+                                         H, e->h);
     VLO_LAUNCH_CHECK();
     count_launch();
   }
@@ -722,8 +730,7 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
     p.last_index = last ? d_last_index : nullptr;
     p.H = H;
     p.eps = c.rms_norm_eps;
-    resid_rmsnorm_kernel<<<T, 256, norm_smem, st>>>(p);
-    VLO_LAUNCH_CHECK();
+    VLO_CUDA(launch_pdl(resid_rmsnorm_kernel, dim3(T), dim3(std::min(1024, std::max(32, H / 4))), norm_smem, st, p));
     count_launch();
     return 0;
   };
@@ -751,8 +758,7 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
       p.v_cache = kv_layer_base(e, l, 1);
       p.n_heads = c.num_heads;
       p.n_kv_heads = c.num_kv_heads;
-      qkv_rope_append_kernel<<<dim3(T, c.num_heads + 2 * c.num_kv_heads), 64, 0, st>>>(p);
-      VLO_LAUNCH_CHECK();
+      VLO_CUDA(launch_pdl(qkv_rope_append_kernel, dim3(T, c.num_heads + 2 * c.num_kv_heads), dim3(64), 0, st, p));
       count_launch();
     }
     if (attn_run(plan, e->q, kv_layer_base(e, l, 0), kv_layer_base(e, l, 1), kv_rows_per_layer(c), e->attn_out,
@@ -770,9 +776,9 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
       p.act = e->act;
       p.T = T;
       p.I = c.intermediate_size;
-      const long long n2 = static_cast<long long>(T) * c.intermediate_size / 2;
-      swiglu_kernel<<<static_cast<int>(std::min<long long>((n2 + 255) / 256, 4 * kNumSMs)), 256, 0, st>>>(p);
-      VLO_LAUNCH_CHECK();
+      const long long n2 = static_cast<long long>(T) * c.intermediate_size / 4;
+      VLO_CUDA(launch_pdl(swiglu_kernel, dim3(static_cast<unsigned>(std::min<long long>((n2 + 255) / 256, 4 * kNumSMs))),
+                          dim3(256), 0, st, p));
       count_launch();
     }
     if (gemm_partial(e, d.down, H, e->act, T, c.intermediate_size, &sk, st)) return -1;
@@ -784,8 +790,8 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
   if (gemm_ws_store16(FMT_BF16, e->lm_head, c.vocab_size, e->xn_last, n_seqs, H, logits, c.vocab_size, nullptr, ACT_NONE, st))
     return -1;
   DecisionOut* dec_out = d_decisions ? reinterpret_cast<DecisionOut*>(d_decisions) : e->decisions;
-  decision_kernel<<<n_seqs, 1024, 0, st>>>(logits, c.vocab_size, interval_id, dec_out);
-  VLO_LAUNCH_CHECK();
+  VLO_CUDA(launch_pdl(decision_kernel, dim3(n_seqs), dim3(1024), 0, st, static_cast<const bf16*>(logits), c.vocab_size,
+                      interval_id, dec_out));
   count_launch();
 
   for (int i = 0; i < n_seqs; ++i) e->kv_len[h_stream_ids[i]] += h_q_lens[i];

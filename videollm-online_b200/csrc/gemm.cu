@@ -219,9 +219,8 @@ int launch_ws(const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsArgs& a,
     const double out_b = a.mode == 0 ? 4.0 * a.rows_x * a.rows_w : 2.0 * a.rows_x * a.rows_w;
     prof_begin(PROF_GEMM_STREAM, stream, 2.0 * a.k * (static_cast<double>(a.rows_w) + a.rows_x) + out_b);
   }
-  kern<<<a.sk.G, kGemmThreads, GemmWsCfg<BN>::kSmemBytes, stream>>>(tw, tx, a);
+  VLO_CUDA(launch_pdl(kern, dim3(a.sk.G), dim3(kGemmThreads), GemmWsCfg<BN>::kSmemBytes, stream, tw, tx, a));
   prof_end(stream);
-  VLO_LAUNCH_CHECK();
   count_launch();
   return 0;
 }

@@ -59,7 +59,7 @@ struct GemmCfg {
   static constexpr int kBytesB = BN * kGemmBK * 2;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
   // 1024 B of slack so the tile ring can be aligned for SWIZZLE_128B.
-  static constexpr int kSmemBytes = kStages * (kBytesA + kBytesB) + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * (kBytesA + kBytesB) + 1024 + 256 + 1024;  // + bias tile
 };
 
 template <int FMT>
@@ -79,8 +79,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     // F.gelu(x, approximate='tanh'), HF:activations.py ("gelu_pytorch_tanh"); fp32 math on
     // the 16-bit input, one rounding at the end.
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-    float inner = k0 * (v + k1 * v * v * v);
-    return r16<FMT>(0.5f * v * (1.0f + tanhf(inner)));
+    const float inner = k0 * (v + k1 * v * v * v);
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(inner));  // MUFU.TANH: |err| ~ 2^-11, below fp16 output resolution
+    return r16<FMT>(0.5f * v * (1.0f + th));
   }
   if (act == ACT_GELU_ERF_PY) {
     // GELUActivation(use_gelu_python=True): x * 0.5 * (1 + erf(x / sqrt(2))) evaluated as four
@@ -172,6 +174,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // -------------------------------------------------- epilogue warps 2..5
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int a_row = m_tile * kGemmBM + q * 32 + lane;
+    // per-column bias of this tile -> shared memory while the mainloop runs (SWAP = false only)
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+    if (!SWAP && EPI != EPI_PARTIAL) {
+      const int et = threadIdx.x - 64;  // 0..127
+      for (int j = et; j < BN; j += 128) {
+        const int col = n_tile * BN + j;
+        s_bias[j] = (p.bias != nullptr && col < p.rows_b) ? __ldg(p.bias + col) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");  // epilogue warps only
+    }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const bool a_ok = a_row < p.rows_a;
@@ -215,8 +227,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int j = 0; j < 16; ++j) {
           float acc = __uint_as_float(v[j]);
           if (EPI != EPI_PARTIAL) {
-            const float bj = (p.bias != nullptr && j < nvalid) ? __ldg(p.bias + b0 + j) : 0.f;
-            acc = r16<FMT>(acc + bj);
+            acc = r16<FMT>(acc + s_bias[c0 + j]);
             if (EPI == EPI_STORE16) acc = apply_act<FMT>(acc, p.act);
           }
           x[j] = acc;

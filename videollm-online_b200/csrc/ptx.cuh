@@ -158,6 +158,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int fmt, int m, int n) {
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with the programmatic-stream-serialization attribute may start while its
+// predecessor in the stream is still running; it must execute pdl_wait() before touching anything the
+// predecessor produces (the wait returns once the predecessor grid has completed and flushed).
+// pdl_trigger() lets the successor start being scheduled; everything before pdl_wait() in the
+// successor (barrier init, TMEM allocation, descriptor prefetch) then overlaps this grid's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // --------------------------------------------------------------- misc math
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));

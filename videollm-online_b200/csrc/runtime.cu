@@ -1,6 +1,7 @@
 // Process-wide runtime bits of libvlo_b200.so: thread-local error text, launch counter and the
 // optional per-kernel-class CUDA-event profiler bench.py uses for its roofline numbers.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -14,6 +15,16 @@ const char* last_error() { return g_err.c_str(); }
 int fail(const std::string& m) {
   set_error(m);
   return -1;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VLO_NO_PDL");
+    on = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  // event-bracketed profiling wants serialised kernels: the per-class times then add up to the step
+  return on == 1 && !prof_on();
 }
 
 static std::atomic<long long> g_launches{0};

@@ -186,15 +186,16 @@ class Engine:
         return out
 
     def step(self, stream_ids: Sequence[int], q_lens: Sequence[int], embeds: torch.Tensor, *,
-             prefix_ids: Optional[torch.Tensor] = None, interval_id: Optional[int] = None,
+             row_ids: Optional[torch.Tensor] = None, interval_id: Optional[int] = None,
              want_logits: bool = True):
-        """KV-append forward of a ragged batch.  Returns (logits [n_seqs, V] bf16 view or None, decisions
+        """KV-append forward of a ragged batch.  `row_ids` (int64 [sum q_lens], optional): id >= 0 -> the row is the
+        embedding of that token (gathered on the device), id < 0 -> the row of `embeds` is used as is.  Returns (logits [n_seqs, V] bf16 view or None, decisions
         device tensor int32 [n_seqs, 8]).  Nothing is synchronised; call `read_decisions` for host values."""
         n = len(stream_ids)
         T = int(sum(q_lens))
         embeds = embeds.contiguous()
         if T > self.max_step_tokens:
-            return self._step_chunked(stream_ids, q_lens, embeds, prefix_ids, interval_id, want_logits)
+            return self._step_chunked(stream_ids, q_lens, embeds, row_ids, interval_id, want_logits)
         if embeds.dtype != torch.bfloat16 or embeds.device != self.device or embeds.numel() != T * self.cfg.hidden_size:
             raise VloError(f"step: embeds must be bf16 [{T},{self.cfg.hidden_size}] on {self.device}")
         sid = (C.c_int32 * n)(*stream_ids)
@@ -204,25 +205,23 @@ class Engine:
             iid = -1
         logits = self._logits[:n] if want_logits else None
         pid = None
-        if prefix_ids is not None:
-            pid = prefix_ids.to(device=self.device, dtype=torch.int64).contiguous()
+        if row_ids is not None:
+            pid = row_ids.to(device=self.device, dtype=torch.int64).contiguous().view(-1)
+            if pid.numel() != T:
+                raise VloError(f"step: row_ids must have one entry per packed row ({T}), got {pid.numel()}")
         check(self.lib.vlo_step_ids(self._h, n, sid, ql, _ptr(pid), _ptr(embeds), _ptr(logits), _ptr(self._dec_dev), iid,
                                     self._stream()), "vlo_step")
         return logits, self._dec_dev[:n]
 
-    def _step_chunked(self, stream_ids, q_lens, embeds, prefix_ids, interval_id, want_logits):
+    def _step_chunked(self, stream_ids, q_lens, embeds, row_ids, interval_id, want_logits):
         """Inputs longer than max_step_tokens (the first frame's system prompt, long queries): feed the KV-append
         forward in pieces — chunked streaming is exactly one causal pass.  Each
         sequence's logits / decision come from the sub-step that holds its last piece."""
         n, cap, H = len(stream_ids), self.max_step_tokens, self.cfg.hidden_size
-        if prefix_ids is not None:  # materialise the gathered prefix rows once; the sub-steps then see plain embeddings
-            embeds = embeds.clone()
-            starts = [int(sum(q_lens[:i])) for i in range(n)]
-            pid = prefix_ids.to(self.device).view(-1)
+        if row_ids is not None:  # materialise the gathered token rows once; the sub-steps then see plain embeddings
+            pid = row_ids.to(self.device).view(-1)
             rows = self.embed_tokens(pid.clamp(min=0))
-            for i, st in enumerate(starts):
-                if int(pid[i]) >= 0:
-                    embeds[st] = rows[i]
+            embeds = torch.where((pid >= 0)[:, None], rows, embeds)
         logits_out = torch.empty(n, self.cfg.vocab_size, dtype=torch.bfloat16, device=self.device) if want_logits else None
         dec_out = torch.empty(n, DECISION_DTYPE_FIELDS, dtype=torch.int32, device=self.device)
         off, done = 0, [0] * n

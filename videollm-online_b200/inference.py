@@ -103,19 +103,14 @@ class LiveInfer:
     def _forward(self, ids: torch.Tensor, frame_embeds: torch.Tensor = None):
         """One KV-append step over [embed(ids) ; frame_embeds]; returns the device decision (host copy)."""
         eng = self.model.engine
-        ids = ids.reshape(-1)
+        ids = ids.reshape(-1).to(torch.int64)
         n_ids = ids.numel()
-        if frame_embeds is not None and n_ids == 1:
-            # steady state: the engine gathers the single prefix row by id
-            packed = torch.empty(1 + frame_embeds.shape[0], self.hidden_size, dtype=torch.bfloat16, device=self.device)
-            packed[1:] = frame_embeds
-            eng.step([self._kv.stream_id], [packed.shape[0]], packed, prefix_ids=ids.to(self.device))
-        else:
-            parts = [self.model.get_input_embeddings()(ids.to(self.device)).view(-1, self.hidden_size)] if n_ids else []
-            if frame_embeds is not None:
-                parts.append(frame_embeds.view(-1, self.hidden_size))
-            packed = torch.cat(parts, 0)
-            eng.step([self._kv.stream_id], [packed.shape[0]], packed)
+        n_fr = 0 if frame_embeds is None else frame_embeds.shape[0]
+        packed = torch.empty(n_ids + n_fr, self.hidden_size, dtype=torch.bfloat16, device=self.device)
+        if n_fr:
+            packed[n_ids:] = frame_embeds.view(-1, self.hidden_size)
+        row_ids = torch.cat([ids, torch.full((n_fr,), -1, dtype=torch.int64)]).to(self.device, non_blocking=True)
+        eng.step([self._kv.stream_id], [n_ids + n_fr], packed, row_ids=row_ids)   # token rows gathered on the device
         self.past_key_values = self._kv
         dec = eng.read_decisions(1)[0]
         if self.decision_hook is not None:
