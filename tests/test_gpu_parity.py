@@ -264,9 +264,9 @@ def test_multistream_scheduler_equals_independent_liveinfer(built, golden, tiny)
     I, E, END = cfg.frame_token_interval_id, cfg.eos_token_id, cfg.stream_end_id
     A, B = 300, 301
     scripts = [  # per-stream call index -> forced token
-        {0: I, 1: END, 2: A, 3: B, 4: E, 5: I, 6: I},
-        {0: END, 1: E, 2: I, 3: END, 4: A, 5: E, 6: I},
-        {0: I, 1: I, 2: I, 3: END, 4: A, 5: A, 6: B, 7: E},
+        {0: I, 1: END, 2: A, 3: B, 4: E, 5: I, 6: I, 7: I},
+        {0: END, 1: E, 2: I, 3: END, 4: A, 5: E, 6: I, 7: I},
+        {0: I, 1: I, 2: I, 3: END, 4: A, 5: A, 6: B, 7: E, 8: I},
     ]
 
     def force(dec, t):

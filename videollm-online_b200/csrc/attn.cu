@@ -3,8 +3,10 @@
 // The plan depends only on (q_len, kv_len) of the sequences, so a decoder step builds and
 // uploads it once and reuses it for all layers.
 #include "attn.cuh"
+#include "attn_tc.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -18,14 +20,24 @@ constexpr size_t kAlign = 256;
 size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 int max_chunks(int total_tokens, int n_seqs, int G) {
-  const int per = 64 / G;
+  const int per = std::max(1, 64 / G);  // v1 chunking (v2 packs twice as many tokens per item)
   return total_tokens / per + n_seqs + 1;
+}
+// kernel generation: 2 = tcgen05 (attn_tc.cuh), 1 = mma.sync (attn.cuh).  VLO_ATTN=1 forces v1 (A/B checks).
+int attn_version(int G) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("VLO_ATTN");
+    forced = (e != nullptr && e[0] == '1') ? 1 : 2;
+  }
+  if (128 % G != 0) return 1;
+  return forced;
 }
 // Per item n_splits <= max(1, 148 / (n_kv_heads * n_items)) and rows <= 64, so the sum of
 // n_kv_heads * n_splits * rows over all items is bounded by (148 + n_kv_heads * n_items) * 64.
 size_t cap_slots_for(int total_tokens, int n_seqs, int n_heads, int n_kv_heads) {
   const int G = n_heads / n_kv_heads;
-  return static_cast<size_t>(kNumSMs + n_kv_heads * max_chunks(total_tokens, n_seqs, G)) * 64;
+  return static_cast<size_t>(kNumSMs + n_kv_heads * max_chunks(total_tokens, n_seqs, G)) * 128;
 }
 }  // namespace
 
@@ -47,7 +59,10 @@ int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, in
   VLO_CHECK(n_heads % n_kv_heads == 0, "n_heads must be a multiple of n_kv_heads");
   const int G = n_heads / n_kv_heads;
   VLO_CHECK(G <= 64, "GQA group too large");
-  const int per = 64 / G;
+  const int version = attn_version(G);
+  const int per = (version == 2 ? 128 : 64) / G;   // query tokens per work item
+  const int blk = version == 2 ? kTcBlk : kAttnBlk;  // keys per pipeline block
+  plan->version = version;
 
   std::vector<AttnItem> items;
   std::vector<int> tok_item(total_tokens, 0);
@@ -76,9 +91,9 @@ int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, in
             static_cast<double>(it.q_count) * n_heads * kAttnHD * 2 * 2;
   plan->algo_bytes = algo;
   for (AttnItem& it : items) {
-    const int nblk = (it.q_pos0 + it.q_count + kAttnBlk - 1) / kAttnBlk;
+    const int nblk = (it.q_pos0 + it.q_count + blk - 1) / blk;
     int bps = (nblk + want - 1) / want;
-    bps = std::max(2, bps + (bps & 1));  // even: both warp groups get the same number of blocks
+    if (version == 1) bps = std::max(2, bps + (bps & 1));  // even: both warp groups get the same number of blocks
     it.blocks_per_split = bps;
     it.n_splits = (nblk + bps - 1) / bps;
     it.ws_slot0 = static_cast<int>(slots);
@@ -111,9 +126,62 @@ int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, in
   return 0;
 }
 
+static int launch_merge(const AttnPlan& plan, void* d_out, int n_heads, int n_kv_heads, float scale_log2, cudaStream_t stream) {
+  AttnMergeParams mp{};
+  mp.ws_o = plan.ws_o;
+  mp.ws_ml = plan.ws_ml;
+  mp.items = static_cast<const AttnItem*>(plan.d_items);
+  mp.tok_item = plan.d_tok_item;
+  mp.out = static_cast<__nv_bfloat16*>(d_out);
+  mp.n_heads = n_heads;
+  mp.n_kv_heads = n_kv_heads;
+  mp.scale_log2 = scale_log2;
+  prof_begin(PROF_ATTN_MERGE, stream, 0.0);
+  VLO_CUDA(launch_pdl(attn_merge_kernel, dim3(n_heads, plan.total_tokens), dim3(128), 0, stream, mp));
+  prof_end(stream);
+  count_launch();
+  return 0;
+}
+
+static int attn_run_tc(const AttnPlan& plan, const void* d_q, const void* d_k, const void* d_v, long long kv_rows,
+                       void* d_out, int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream) {
+  CUtensorMap tk, tv;
+  if (tmap_2d_sw128(d_k, static_cast<int>(kv_rows), kAttnHD, kTcBlk, 1, &tk) != 0) return -1;
+  if (tmap_2d_sw128(d_v, static_cast<int>(kv_rows), kAttnHD, kTcBlk, 1, &tv) != 0) return -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLO_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    attr_set = true;
+  }
+  const float scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(head_dim)));
+  AttnTcParams p{};
+  p.base.q = static_cast<const __nv_bfloat16*>(d_q);
+  p.base.ws_o = plan.ws_o;
+  p.base.ws_ml = plan.ws_ml;
+  p.base.items = static_cast<const AttnItem*>(plan.d_items);
+  p.base.n_heads = n_heads;
+  p.base.n_kv_heads = n_kv_heads;
+  p.base.scale_log2 = scale_log2;
+  // V tile = MN-major B operand: 64-d halves 16 KB apart (LBO), 8-key groups 1 KB apart (SBO)
+  static int swap_ls = -1;
+  if (swap_ls < 0) {
+    const char* e = getenv("VLO_ATTN_VDESC");
+    swap_ls = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  p.v_lbo = swap_ls ? 1024u : static_cast<uint32_t>(kTcSub);
+  p.v_sbo = swap_ls ? static_cast<uint32_t>(kTcSub) : 1024u;
+  prof_begin(PROF_ATTN, stream, plan.algo_bytes);
+  VLO_CUDA(launch_pdl(attn_tc_kernel, dim3(plan.max_splits, n_kv_heads, plan.n_items), dim3(kTcThreads), kTcSmemBytes, stream,
+                      tk, tv, p));
+  prof_end(stream);
+  count_launch();
+  return launch_merge(plan, d_out, n_heads, n_kv_heads, scale_log2, stream);
+}
+
 int attn_run(const AttnPlan& plan, const void* d_q, const void* d_k, const void* d_v, long long kv_rows, void* d_out,
              int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream) {
   VLO_CHECK(kv_rows > 0 && kv_rows < (1ll << 31), "KV matrix rows out of range for a TMA map");
+  if (plan.version == 2) return attn_run_tc(plan, d_q, d_k, d_v, kv_rows, d_out, n_heads, n_kv_heads, head_dim, stream);
   CUtensorMap tk, tv;
   if (tmap_2d_sw128(d_k, static_cast<int>(kv_rows), kAttnHD, kAttnBlk, 1, &tk) != 0) return -1;
   if (tmap_2d_sw128(d_v, static_cast<int>(kv_rows), kAttnHD, kAttnBlk, 1, &tv) != 0) return -1;

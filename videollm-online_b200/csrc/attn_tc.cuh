@@ -1,0 +1,336 @@
+// KV-append attention, tcgen05 version (v2) — same contract, work items, split-KV plan and partial
+// (m, l, O) workspace as attn.cuh, different engine room:
+//
+//   S = Q K^T and O += P V run on the 5th-gen tensor cores (tcgen05.mma, M = 128, N = 128, fp32 accumulators in
+//   TMEM), so K and V are read from shared memory exactly once by the MMA unit instead of 3-4x through ldmatrix.
+//   The <= 128/G query tokens x G heads of a kv head occupy TMEM lanes  lane = g * (128/G) + t,  one softmax
+//   thread per lane: row max / exp2 / row sum need no shuffles.
+//
+//   warp 0      TMA producer: per 128-key block one stage = K [128 keys x 128 d] + V [128 keys x 128 d] (64 KB), 2 stages
+//   warp 1      MMA issuer:   S_j -> TMEM S[j&1];  after P_j is staged: O += P_j V_j      (software-pipelined: S_{j+1} first)
+//   warps 2-5   softmax:      tcgen05.ld S row -> online softmax with lazy (threshold) rescaling of O in TMEM ->
+//                             P_j as bf16 into a 128B-swizzled K-major smem tile (double buffered) -> epilogue
+//   K tile: K-major B operand (same descriptor as the GEMMs).  V tile: rows = keys, d contiguous -> MN-major B operand.
+#pragma once
+#include <cuda.h>
+#include "attn.cuh"
+#include "ptx.cuh"
+
+namespace vlo {
+
+constexpr int kTcBlk = 128;                          // keys per block
+constexpr int kTcStages = 2;
+constexpr int kTcSub = kTcBlk * 128;                 // one [128 rows x 64 elem] swizzled sub-tile = 16 KB
+constexpr int kTcStageBytes = 4 * kTcSub;            // K(2 d-halves) + V(2 d-halves) = 64 KB
+constexpr int kTcQBytes = 2 * kTcSub;                // Q tile 32 KB
+constexpr int kTcPBytes = 2 * kTcSub;                // one P buffer 32 KB
+constexpr int kTcSmemBytes = kTcQBytes + 2 * kTcPBytes + kTcStages * kTcStageBytes + 1024 + 256;
+constexpr int kTcThreads = 192;
+constexpr float kTcRescaleLog2 = 8.0f;               // rescale O only when the row max grew by > 2^8
+
+// tcgen05.st / ld, 32 lanes x 32 columns
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+      "%25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+// MN-major, 128B-swizzled B operand (V tile: rows = keys (K), 64 contiguous d (N) per 128-byte row, the
+// second 64-d half `lbo_bytes` further; 8-key groups `sbo_bytes` apart).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, A K-major, B K-major or MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+struct AttnTcParams {
+  AttnParams base;
+  uint32_t v_lbo, v_sbo;  // V descriptor strides (bytes)
+};
+
+// swizzled byte offset of 16-byte chunk `c16` (0..15 along the 128-element row) of row `r` in a
+// [2 sub-tiles][128 rows][128 B] K-major tile
+__device__ __forceinline__ uint32_t tc_sw_off(int r, int c16) {
+  return static_cast<uint32_t>((c16 >> 3) * kTcSub + r * 128 + (((c16 & 7) ^ (r & 7)) << 4));
+}
+
+// grid = (max_splits, n_kv_heads, n_items); block = 192.
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnTcParams pp) {
+  const AttnParams& p = pp.base;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* q_tile = smem;
+  uint8_t* p_tile = smem + kTcQBytes;                       // 2 buffers
+  uint8_t* kv_tile = p_tile + 2 * kTcPBytes;                // kTcStages stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_tile + kTcStages * kTcStageBytes);
+  uint64_t* kv_full = bars;                  // [stages]  TMA -> MMA
+  uint64_t* kv_empty = kv_full + kTcStages;  // [stages]  PV done -> TMA
+  uint64_t* s_full = kv_empty + kTcStages;   // [2]       S_j in TMEM
+  uint64_t* s_empty = s_full + 2;            // [2]       softmax has read S_j
+  uint64_t* p_full = s_empty + 2;            // [2]       P_j staged in smem (and O rescaled)
+  uint64_t* p_empty = p_full + 2;            // [2]       PV_j done reading P buffer
+  uint64_t* o_done = p_empty + 2;            // [1]       PV_j complete (phase j)
+  uint64_t* q_ready = o_done + 1;            // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    for (int i = 0; i < kTcStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_done, 1);
+    mbar_init(q_ready, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  const AttnItem it = p.items[blockIdx.z];
+  const int split = blockIdx.x;
+  const int kvh = blockIdx.y;
+  const int G = p.n_heads / p.n_kv_heads;
+  const int rph = 128 / G;  // TMEM lanes (rows) per query head
+  const int kv_end = it.q_pos0 + it.q_count;
+  const int nblk_total = (kv_end + kTcBlk - 1) / kTcBlk;
+  const int blk0 = split * it.blocks_per_split;
+  const int nblk = (split < it.n_splits) ? min(blk0 + it.blocks_per_split, nblk_total) - blk0 : 0;
+  const uint32_t tS = tmem_base, tO = tmem_base + 256;
+
+  if (nblk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // ------------------------------------------------------------ TMA producer
+        const int row_base = it.kv_row0 + kvh * it.kv_head_stride;
+        for (int j = 0; j < nblk; ++j) {
+          const int s = j % kTcStages;
+          const uint32_t ph = (j / kTcStages) & 1;
+          mbar_wait(&kv_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], kTcStageBytes);
+          uint8_t* st = kv_tile + s * kTcStageBytes;
+          const int row = row_base + (blk0 + j) * kTcBlk;
+          tma_load_2d(st, &tm_k, &kv_full[s], 0, row, kEvictFirst);
+          tma_load_2d(st + kTcSub, &tm_k, &kv_full[s], 64, row, kEvictFirst);
+          tma_load_2d(st + 2 * kTcSub, &tm_v, &kv_full[s], 0, row, kEvictFirst);
+          tma_load_2d(st + 3 * kTcSub, &tm_v, &kv_full[s], 64, row, kEvictFirst);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 1);
+        const uint32_t q_addr = smem_u32(q_tile);
+        mbar_wait(q_ready, 0);
+        tc_fence_after();
+        auto issue_pv = [&](int i) {
+          const int s = i % kTcStages;
+          const int b = i & 1;
+          mbar_wait(&p_full[b], (i >> 1) & 1);
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(p_tile + b * kTcPBytes);
+          const uint32_t v_addr = smem_u32(kv_tile + s * kTcStageBytes + 2 * kTcSub);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA
+            const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * kTcSub + (kk & 3) * 32);
+            const uint64_t db = umma_desc_mn_sw128(v_addr + kk * 16 * 128, pp.v_lbo, pp.v_sbo);
+            umma_f16(tO, da, db, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[s]);
+          umma_commit(&p_empty[b]);
+          umma_commit(o_done);
+        };
+        for (int j = 0; j < nblk; ++j) {
+          const int s = j % kTcStages;
+          const int b = j & 1;
+          mbar_wait(&kv_full[s], (j / kTcStages) & 1);
+          mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(kv_tile + s * kTcStageBytes);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {  // 16 dims per MMA
+            const uint64_t da = umma_desc_sw128(q_addr + (kk >> 2) * kTcSub + (kk & 3) * 32);
+            const uint64_t db = umma_desc_sw128(k_addr + (kk >> 2) * kTcSub + (kk & 3) * 32);
+            umma_f16(tS + b * 128, da, db, idesc_s, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[b]);
+          if (j >= 1) issue_pv(j - 1);
+        }
+        issue_pv(nblk - 1);
+      }
+    } else {
+      // -------------------------------------------------------------- softmax / correction / epilogue warps
+      const int q = warp & 3;
+      const int r = q * 32 + lane;       // TMEM lane == tile row
+      const int g = r / rph, t = r % rph;
+      const bool valid = (g < G) && (t < it.q_count);
+      const int lim = valid ? it.q_pos0 + t : -1;  // last visible key (causal with offset)
+      const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+      // ---- stage Q: this thread's row, 16 chunks of 16 B, swizzled K-major; invalid rows are zero
+      {
+        const uint4* src = valid ? reinterpret_cast<const uint4*>(
+                                       p.q + (static_cast<size_t>(it.q_tok0 + t) * p.n_heads + kvh * G + g) * kAttnHD)
+                                 : nullptr;
+#pragma unroll
+        for (int c16 = 0; c16 < 16; ++c16) {
+          const uint4 v = valid ? __ldg(src + c16) : make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(q_tile + tc_sw_off(r, c16)) = v;
+        }
+        fence_proxy_async();
+        mbar_arrive(q_ready);
+      }
+      const float c = p.scale_log2;
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nblk; ++j) {
+        const int b = j & 1;
+        mbar_wait(&s_full[b], (j >> 1) & 1);
+        tc_fence_after();
+        const int key0 = (blk0 + j) * kTcBlk;
+        const bool need_mask = key0 + kTcBlk - 1 > it.q_pos0;  // block reaches past the first query's limit
+        // pass 1: row max (S stays in TMEM; it is re-read in pass 2)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tS + lane_addr + b * 128 + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float s = __uint_as_float(v[i]);
+            if (need_mask && key0 + c0 + i > lim) s = -INFINITY;
+            mx = fmaxf(mx, s);
+          }
+        }
+        if (!need_mask && !valid) mx = -INFINITY;
+        // lazy rescale: keep the old reference max unless the new one is much larger
+        const float m_new = fmaxf(m_ref, mx);
+        const bool grow = (m_ref == -INFINITY) ? (m_new != -INFINITY) : ((m_new - m_ref) * c > kTcRescaleLog2);
+        const float m_use = grow ? m_new : m_ref;
+        const float alpha = (grow && m_ref != -INFINITY) ? exp2f((m_ref - m_new) * c) : 1.f;
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+          // O of this warp's 32 lanes must be rescaled: wait until PV_{j-1} has landed in TMEM
+          mbar_wait(o_done, (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_x32(tO + lane_addr + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_x32(tO + lane_addr + c0, v);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+        }
+        m_ref = m_use;
+        const float moff = (m_ref == -INFINITY) ? 0.f : m_ref * c;
+        // pass 2: P = exp2(S c - m c) -> bf16 -> swizzled smem tile; wait for the P buffer to be free first
+        mbar_wait(&p_empty[b], ((j >> 1) & 1) ^ 1);
+        uint8_t* pt = p_tile + b * kTcPBytes;
+        float ps = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tS + lane_addr + b * 128 + c0, v);
+          tmem_ld_wait();
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+            if (need_mask) {
+              if (key0 + c0 + i > lim) s0 = -INFINITY;
+              if (key0 + c0 + i + 1 > lim) s1 = -INFINITY;
+            } else if (!valid) {
+              s0 = s1 = -INFINITY;
+            }
+            const float p0 = exp2f(s0 * c - moff), p1 = exp2f(s1 * c - moff);
+            ps += p0 + p1;
+            w[i >> 1] = pack_bf16(p0, p1);
+          }
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            *reinterpret_cast<uint4*>(pt + tc_sw_off(r, (c0 >> 3) + k4)) = make_uint4(w[4 * k4], w[4 * k4 + 1], w[4 * k4 + 2], w[4 * k4 + 3]);
+        }
+        l_run += ps;
+        tc_fence_before();
+        mbar_arrive(&s_empty[b]);   // S[b] may be overwritten by block j+2
+        fence_proxy_async();        // make the generic-proxy P writes visible to the MMA (async proxy)
+        mbar_arrive(&p_full[b]);
+      }
+      // ---- epilogue: partial (m, l, O) of this split; merged by attn_merge_kernel
+      mbar_wait(o_done, (nblk - 1) & 1);
+      tc_fence_after();
+      const int rows = it.q_count * G;
+      const int rr = t * G + g;  // row index inside the item, same convention as v1 / the merge kernel
+      const size_t slot = static_cast<size_t>(it.ws_slot0) + (static_cast<size_t>(kvh) * it.n_splits + split) * rows + rr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tO + lane_addr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(p.ws_o + slot * kAttnHD + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                 __uint_as_float(v[4 * i + 3]));
+        }
+      }
+      if (valid) {
+        p.ws_ml[slot * 2] = m_ref;
+        p.ws_ml[slot * 2 + 1] = l_run;
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace vlo

@@ -134,6 +134,7 @@ struct AttnPlan {
   void* d_items;
   int* d_tok_item;
   int n_items, max_splits, total_tokens;
+  int version;        // 1 = mma.sync kernel, 2 = tcgen05 kernel
   double algo_bytes;  // algorithmic HBM bytes of one attn_run over this plan (K+V rows read, Q read, out written)
 };
 // Build the work-item plan on the host and enqueue its upload.  h_stage (>= attn_stage_bytes())
