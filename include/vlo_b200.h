@@ -145,18 +145,22 @@ int vlo_last_step_hidden(vlo_engine* e, void* d_hidden, void* cuda_stream);
 int vlo_op_gemm(int fmt, int swap, int epi, int act, const void* d_a, int rows_a, const void* d_b, int rows_b, int k,
                 void* d_out, int ld_out, const float* d_bias, const float* d_pos, int pos_rows, int splits,
                 long long split_stride, int bn, void* cuda_stream);
-/* Persistent weight-streaming GEMM (csrc/gemm_ws.cuh): out[t, n] = sum_k X[t,k] W[n,k], rows_x <= 128.
+/* Persistent weight-streaming GEMM (csrc/gemm_ws.cuh): out[t, n] = sum_k X[t,k] W[n,k].  bn = token-tile width
+ * (0: smallest of 16/32/64/128 covering rows_x, which must then be <= 128; 64/96/128/192 tile larger rows_x).
  * mode 0: stream-K over all SMs, fp32 partial planes out[plane][rows_x][rows_w] (the caller zero-fills d_out
  *         and sums the planes; *h_max_planes tells how many planes to provide); d_out == NULL only plans.
  * mode 1: whole tiles, 16-bit out[rows_x][ld_out] = act(acc + bias). */
 int vlo_op_gemm_ws(int fmt, int mode, const void* d_w, int rows_w, const void* d_x, int rows_x, int k, void* d_out,
-                   int ld_out, long long plane_stride, const float* d_bias, int act, int n_ctas, int* h_max_planes,
+                   int ld_out, long long plane_stride, const float* d_bias, int act, int n_ctas, int bn, int* h_max_planes,
                    void* cuda_stream);
 /* KV-append attention over one layer's cache (the graded kernel, K15):
  *   d_q bf16 [n_tok, n_heads, head_dim] (RoPE applied); d_k/d_v bf16 [n_kv_heads, kv_stride, head_dim];
  *   keys 0..kv_len-1 valid, the n_tok query tokens sit at positions kv_len-n_tok .. kv_len-1 (causal with
  *   offset, HF:masking_utils.py:263-272); d_out bf16 [n_tok, n_heads*head_dim]; d_ws fp32 scratch of
  *   vlo_op_attn_ws_bytes(). Replaces HF:models/llama/modeling_llama.py:272-285 (SDPA / flash-attn 2). */
+/* which generation of the KV-append attention kernel runs for this head layout: 2 = tcgen05 (csrc/attn_tc.cuh),
+ * 1 = mma.sync (csrc/attn.cuh; forced by VLO_ATTN=1, or when n_heads/n_kv_heads does not divide 128) */
+int vlo_op_attn_version(int n_heads, int n_kv_heads);
 int64_t vlo_op_attn_ws_bytes(int n_tok, int n_heads, int head_dim, int kv_len);
 int vlo_op_attn_kvappend(const void* d_q, const void* d_k, const void* d_v, void* d_out, float* d_ws, int n_tok,
                          int n_heads, int n_kv_heads, int head_dim, int kv_len, long long kv_stride, void* cuda_stream);

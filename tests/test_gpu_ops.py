@@ -158,9 +158,9 @@ def test_gemm_ws_streamk_partials(lib, T, N, K, G):
     planes = C.c_int(0)
     p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    check(lib.vlo_op_gemm_ws(1, 0, p(w), N, p(x), T, K, None, N, T * N, None, 0, G, C.byref(planes), st), "plan")
+    check(lib.vlo_op_gemm_ws(1, 0, p(w), N, p(x), T, K, None, N, T * N, None, 0, G, 0, C.byref(planes), st), "plan")
     ws = torch.zeros(planes.value, T, N, device="cuda")
-    check(lib.vlo_op_gemm_ws(1, 0, p(w), N, p(x), T, K, p(ws), N, T * N, None, 0, G, C.byref(planes), st), "gemm_ws")
+    check(lib.vlo_op_gemm_ws(1, 0, p(w), N, p(x), T, K, p(ws), N, T * N, None, 0, G, 0, C.byref(planes), st), "gemm_ws")
     torch.cuda.synchronize()
     ref = x.float() @ w.float().t()
     assert (ws.sum(0) - ref).abs().max() <= 2e-3 * ref.abs().max()
@@ -179,7 +179,7 @@ def test_gemm_ws_tiles_store16(lib, T, N, K, act):
     out = torch.zeros(T, N, device="cuda", dtype=torch.bfloat16)
     p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    check(lib.vlo_op_gemm_ws(1, 1, p(w), N, p(x), T, K, p(out), N, 0, p(bias), act, 0, None, st), "gemm_ws")
+    check(lib.vlo_op_gemm_ws(1, 1, p(w), N, p(x), T, K, p(out), N, 0, p(bias), act, 0, 0, None, st), "gemm_ws")
     torch.cuda.synchronize()
     y = (x.float() @ w.float().t() + bias).bfloat16()
     if act == 2:
@@ -187,3 +187,31 @@ def test_gemm_ws_tiles_store16(lib, T, N, K, act):
     elif act == 1:
         y = torch.nn.functional.gelu(y.float(), approximate="tanh").bfloat16()
     assert (out.float() - y.float()).abs().max() <= 1e-2 * y.float().abs().max()
+
+
+@pytest.mark.parametrize("M,N,K,bn,mode", [(576, 3072, 1024, 96, 1), (576, 4096, 1024, 64, 1), (576, 1024, 4096, 192, 0),
+                                           (576, 1024, 1024, 192, 0), (1152, 4096, 1024, 192, 1), (300, 200, 256, 128, 1),
+                                           (36, 384, 128, 64, 0)])
+def test_gemm_ws_vit_shapes_fp16(lib, M, N, K, bn, mode):
+    """ViT trunk on the persistent kernel: token rows tiled along MMA-N (bn = 64/96/128/192), fp16"""
+    from videollm_online_b200._lib import check
+    torch.manual_seed(M + N)
+    w = (torch.randn(N, K, device="cuda") * 0.05).half()
+    x = torch.randn(M, K, device="cuda").half()
+    bias = torch.randn(N, device="cuda")
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lin = x.float() @ w.float().t()
+    if mode == 1:
+        out = torch.zeros(M, N, device="cuda", dtype=torch.float16)
+        check(lib.vlo_op_gemm_ws(0, 1, p(w), N, p(x), M, K, p(out), N, 0, p(bias), 1, 0, bn, None, st), "gemm_ws")
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.gelu((lin + bias).half().float(), approximate="tanh")
+        assert (out.float() - ref).abs().max() <= 1e-2 * ref.abs().max()
+    else:
+        planes = C.c_int(0)
+        check(lib.vlo_op_gemm_ws(0, 0, p(w), N, p(x), M, K, None, N, M * N, None, 0, 0, bn, C.byref(planes), st), "plan")
+        ws = torch.zeros(planes.value, M, N, device="cuda")
+        check(lib.vlo_op_gemm_ws(0, 0, p(w), N, p(x), M, K, p(ws), N, M * N, None, 0, 0, bn, C.byref(planes), st), "gemm_ws")
+        torch.cuda.synchronize()
+        assert (ws.sum(0) - lin).abs().max() <= 2e-3 * lin.abs().max()

@@ -15,10 +15,10 @@ for name, (N, K) in {"qkv": (6144, 4096), "o": (4096, 4096), "gate_up": (28672, 
         w = (torch.randn(N, K, device=dev) * 0.02).bfloat16(); x = torch.randn(T, K, device=dev).bfloat16()
         mode = 1 if name == "lm_head" else 0
         planes = C.c_int(1)
-        lib.vlo_op_gemm_ws(1, mode, p(w), N, p(x), T, K, None, N, T * N, None, 0, 0, C.byref(planes), st())
+        lib.vlo_op_gemm_ws(1, mode, p(w), N, p(x), T, K, None, N, T * N, None, 0, 0, 0, C.byref(planes), st())
         out = torch.zeros(planes.value, T, N, device=dev) if mode == 0 else torch.zeros(T, N, device=dev, dtype=torch.bfloat16)
         def run():
-            rc = lib.vlo_op_gemm_ws(1, mode, p(w), N, p(x), T, K, p(out), N, T * N, None, 0, 0, C.byref(planes), st())
+            rc = lib.vlo_op_gemm_ws(1, mode, p(w), N, p(x), T, K, p(out), N, T * N, None, 0, 0, 0, C.byref(planes), st())
             assert rc == 0, lib.vlo_last_error()
         for _ in range(3): run()
         ts = []

@@ -24,7 +24,7 @@ int max_chunks(int total_tokens, int n_seqs, int G) {
   return total_tokens / per + n_seqs + 1;
 }
 // kernel generation: 2 = tcgen05 (attn_tc.cuh), 1 = mma.sync (attn.cuh).  VLO_ATTN=1 forces v1 (A/B checks).
-int attn_version(int G) {
+int attn_version_impl(int G) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("VLO_ATTN");
@@ -40,6 +40,8 @@ size_t cap_slots_for(int total_tokens, int n_seqs, int n_heads, int n_kv_heads) 
   return static_cast<size_t>(kNumSMs + n_kv_heads * max_chunks(total_tokens, n_seqs, G)) * 128;
 }
 }  // namespace
+
+int attn_version(int n_heads, int n_kv_heads) { return attn_version_impl(n_heads / n_kv_heads); }
 
 size_t attn_stage_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads) {
   const int G = n_heads / n_kv_heads;
@@ -59,7 +61,7 @@ int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, in
   VLO_CHECK(n_heads % n_kv_heads == 0, "n_heads must be a multiple of n_kv_heads");
   const int G = n_heads / n_kv_heads;
   VLO_CHECK(G <= 64, "GQA group too large");
-  const int version = attn_version(G);
+  const int version = attn_version_impl(G);
   const int per = (version == 2 ? 128 : 64) / G;   // query tokens per work item
   const int blk = version == 2 ? kTcBlk : kAttnBlk;  // keys per pipeline block
   plan->version = version;

@@ -21,7 +21,8 @@ namespace vlo {
 constexpr int kTcBlk = 128;                          // keys per block
 constexpr int kTcStages = 2;
 constexpr int kTcSub = kTcBlk * 128;                 // one [128 rows x 64 elem] swizzled sub-tile = 16 KB
-constexpr int kTcStageBytes = 4 * kTcSub;            // K(2 d-halves) + V(2 d-halves) = 64 KB
+constexpr int kTcStageBytes = 4 * kTcSub;            // K(2 d-halves) + V(2 d-halves) = 64 KB (K and V rings, 32 KB slots)
+constexpr int kTcHalf = 2 * kTcSub;                  // one K or V tile: 32 KB
 constexpr int kTcQBytes = 2 * kTcSub;                // Q tile 32 KB
 constexpr int kTcPBytes = 2 * kTcSub;                // one P buffer 32 KB
 constexpr int kTcSmemBytes = kTcQBytes + 2 * kTcPBytes + kTcStages * kTcStageBytes + 1024 + 256;
@@ -92,9 +93,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   uint8_t* p_tile = smem + kTcQBytes;                       // 2 buffers
   uint8_t* kv_tile = p_tile + 2 * kTcPBytes;                // kTcStages stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(kv_tile + kTcStages * kTcStageBytes);
-  uint64_t* kv_full = bars;                  // [stages]  TMA -> MMA
-  uint64_t* kv_empty = kv_full + kTcStages;  // [stages]  PV done -> TMA
-  uint64_t* s_full = kv_empty + kTcStages;   // [2]       S_j in TMEM
+  uint64_t* k_full = bars;                   // [stages]  TMA -> MMA (K tile landed)
+  uint64_t* k_empty = k_full + kTcStages;    // [stages]  S_j done -> TMA   (K freed as soon as QK^T has run)
+  uint64_t* v_full = k_empty + kTcStages;    // [stages]  TMA -> MMA (V tile landed)
+  uint64_t* v_empty = v_full + kTcStages;    // [stages]  PV_j done -> TMA
+  uint64_t* s_full = v_empty + kTcStages;    // [2]       S_j in TMEM
   uint64_t* s_empty = s_full + 2;            // [2]       softmax has read S_j
   uint64_t* p_full = s_empty + 2;            // [2]       P_j staged in smem (and O rescaled)
   uint64_t* p_empty = p_full + 2;            // [2]       PV_j done reading P buffer
@@ -107,8 +110,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     for (int i = 0; i < kTcStages; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -147,14 +152,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         for (int j = 0; j < nblk; ++j) {
           const int s = j % kTcStages;
           const uint32_t ph = (j / kTcStages) & 1;
-          mbar_wait(&kv_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&kv_full[s], kTcStageBytes);
           uint8_t* st = kv_tile + s * kTcStageBytes;
           const int row = row_base + (blk0 + j) * kTcBlk;
-          tma_load_2d(st, &tm_k, &kv_full[s], 0, row, kEvictFirst);
-          tma_load_2d(st + kTcSub, &tm_k, &kv_full[s], 64, row, kEvictFirst);
-          tma_load_2d(st + 2 * kTcSub, &tm_v, &kv_full[s], 0, row, kEvictFirst);
-          tma_load_2d(st + 3 * kTcSub, &tm_v, &kv_full[s], 64, row, kEvictFirst);
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[s], kTcHalf);
+          tma_load_2d(st, &tm_k, &k_full[s], 0, row, kEvictFirst);
+          tma_load_2d(st + kTcSub, &tm_k, &k_full[s], 64, row, kEvictFirst);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[s], kTcHalf);
+          tma_load_2d(st + 2 * kTcSub, &tm_v, &v_full[s], 0, row, kEvictFirst);
+          tma_load_2d(st + 3 * kTcSub, &tm_v, &v_full[s], 64, row, kEvictFirst);
         }
       }
     } else if (warp == 1) {
@@ -168,6 +175,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         auto issue_pv = [&](int i) {
           const int s = i % kTcStages;
           const int b = i & 1;
+          mbar_wait(&v_full[s], (i / kTcStages) & 1);
           mbar_wait(&p_full[b], (i >> 1) & 1);
           tc_fence_after();
           const uint32_t p_addr = smem_u32(p_tile + b * kTcPBytes);
@@ -178,14 +186,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
             const uint64_t db = umma_desc_mn_sw128(v_addr + kk * 16 * 128, pp.v_lbo, pp.v_sbo);
             umma_f16(tO, da, db, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&kv_empty[s]);
+          umma_commit(&v_empty[s]);
           umma_commit(&p_empty[b]);
           umma_commit(o_done);
         };
         for (int j = 0; j < nblk; ++j) {
           const int s = j % kTcStages;
           const int b = j & 1;
-          mbar_wait(&kv_full[s], (j / kTcStages) & 1);
+          mbar_wait(&k_full[s], (j / kTcStages) & 1);
           mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t k_addr = smem_u32(kv_tile + s * kTcStageBytes);
@@ -195,6 +203,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
             const uint64_t db = umma_desc_sw128(k_addr + (kk >> 2) * kTcSub + (kk & 3) * 32);
             umma_f16(tS + b * 128, da, db, idesc_s, kk > 0 ? 1u : 0u);
           }
+          umma_commit(&k_empty[s]);  // K tile is free as soon as QK^T has retired
           umma_commit(&s_full[b]);
           if (j >= 1) issue_pv(j - 1);
         }
@@ -229,21 +238,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         tc_fence_after();
         const int key0 = (blk0 + j) * kTcBlk;
         const bool need_mask = key0 + kTcBlk - 1 > it.q_pos0;  // block reaches past the first query's limit
-        // pass 1: row max (S stays in TMEM; it is re-read in pass 2)
-        float mx = -INFINITY;
-#pragma unroll 1
+        // S row -> registers (128 fp32), masked, row max
+        float sv[128];
+#pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t v[32];
           tmem_ld_x32(tS + lane_addr + b * 128 + c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float s = __uint_as_float(v[i]);
-            if (need_mask && key0 + c0 + i > lim) s = -INFINITY;
-            mx = fmaxf(mx, s);
-          }
+          for (int i = 0; i < 32; ++i) sv[c0 + i] = __uint_as_float(v[i]);
         }
-        if (!need_mask && !valid) mx = -INFINITY;
+        tc_fence_before();
+        mbar_arrive(&s_empty[b]);   // S[b] may be overwritten by block j+2
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (key0 + i > lim) sv[i] = -INFINITY;
+        } else if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i) sv[i] = -INFINITY;
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, sv[i]);
         // lazy rescale: keep the old reference max unless the new one is much larger
         const float m_new = fmaxf(m_ref, mx);
         const bool grow = (m_ref == -INFINITY) ? (m_new != -INFINITY) : ((m_new - m_ref) * c > kTcRescaleLog2);
@@ -263,40 +280,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
             tmem_st_x32(tO + lane_addr + c0, v);
           }
           tmem_st_wait();
+          tc_fence_before();
           l_run *= alpha;
         }
         m_ref = m_use;
         const float moff = (m_ref == -INFINITY) ? 0.f : m_ref * c;
-        // pass 2: P = exp2(S c - m c) -> bf16 -> swizzled smem tile; wait for the P buffer to be free first
+        // P = exp2(S c - m c) -> bf16 -> swizzled smem tile; wait for the P buffer to be free first
         mbar_wait(&p_empty[b], ((j >> 1) & 1) ^ 1);
         uint8_t* pt = p_tile + b * kTcPBytes;
         float ps = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(tS + lane_addr + b * 128 + c0, v);
-          tmem_ld_wait();
-          uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-            if (need_mask) {
-              if (key0 + c0 + i > lim) s0 = -INFINITY;
-              if (key0 + c0 + i + 1 > lim) s1 = -INFINITY;
-            } else if (!valid) {
-              s0 = s1 = -INFINITY;
-            }
-            const float p0 = exp2f(s0 * c - moff), p1 = exp2f(s1 * c - moff);
+        for (int c16 = 0; c16 < 16; ++c16) {
+          uint32_t w[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float p0 = exp2f(sv[c16 * 8 + 2 * k] * c - moff), p1 = exp2f(sv[c16 * 8 + 2 * k + 1] * c - moff);
             ps += p0 + p1;
-            w[i >> 1] = pack_bf16(p0, p1);
+            w[k] = pack_bf16(p0, p1);
           }
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            *reinterpret_cast<uint4*>(pt + tc_sw_off(r, (c0 >> 3) + k4)) = make_uint4(w[4 * k4], w[4 * k4 + 1], w[4 * k4 + 2], w[4 * k4 + 3]);
+          *reinterpret_cast<uint4*>(pt + tc_sw_off(r, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         l_run += ps;
-        tc_fence_before();
-        mbar_arrive(&s_empty[b]);   // S[b] may be overwritten by block j+2
         fence_proxy_async();        // make the generic-proxy P writes visible to the MMA (async proxy)
         mbar_arrive(&p_full[b]);
       }

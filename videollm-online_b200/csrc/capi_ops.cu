@@ -61,7 +61,7 @@ int vlo_op_gemm(int fmt, int swap, int epi, int act, const void* d_a, int rows_a
 extern "C" {
 
 int vlo_op_gemm_ws(int fmt, int mode, const void* d_w, int rows_w, const void* d_x, int rows_x, int k, void* d_out,
-                   int ld_out, long long plane_stride, const float* d_bias, int act, int n_ctas, int* h_max_planes,
+                   int ld_out, long long plane_stride, const float* d_bias, int act, int n_ctas, int bn, int* h_max_planes,
                    void* cuda_stream) {
   GemmWsCall c{};
   c.fmt = fmt;
@@ -77,11 +77,16 @@ int vlo_op_gemm_ws(int fmt, int mode, const void* d_w, int rows_w, const void* d
   c.bias = d_bias;
   c.act = act;
   int planes = 1;
-  gemm_ws_plan(rows_w, k, mode, n_ctas, &c.sk, &planes);
+  c.bn = bn;
+  c.weights_hot = rows_x > 128;
+  const int eff_bn = bn > 0 ? bn : (rows_x <= 16 ? 16 : (rows_x <= 32 ? 32 : (rows_x <= 64 ? 64 : 128)));
+  gemm_ws_plan(rows_w, k, mode, n_ctas, &c.sk, &planes, (rows_x + eff_bn - 1) / eff_bn);
   if (h_max_planes) *h_max_planes = planes;
   if (d_out == nullptr) return 0;  // planning query only
   return gemm_ws_launch(c, static_cast<cudaStream_t>(cuda_stream));
 }
+
+int vlo_op_attn_version(int n_heads, int n_kv_heads) { return attn_version(n_heads, n_kv_heads); }
 
 int64_t vlo_op_attn_ws_bytes(int n_tok, int n_heads, int head_dim, int kv_len) {
   (void)head_dim;

@@ -112,9 +112,11 @@ struct GemmWsCall {
   const float* bias;
   int act;
   SkInfo sk;          // from gemm_ws_plan
+  int bn;             // token-tile width (0 = smallest of 16/32/64/128 covering rows_x); 96 / 192 for the ViT
+  int weights_hot;    // 1: weights are re-read by several token tiles (keep them in L2)
 };
 // decomposition for (rows_w, k): n_ctas <= 0 -> one CTA per SM; max_planes = fp32 planes the partials need
-int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_planes);
+int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_planes, int x_tiles = 1);
 int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream);
 
 // ---- attention (attn.cu) ------------------------------------------------------------
@@ -128,6 +130,7 @@ struct AttnSeq {
 // bytes of scratch attn_launch needs for these sequences (upper bound)
 size_t attn_ws_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads);
 size_t attn_stage_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads);
+int attn_version(int n_heads, int n_kv_heads);  // 2 = tcgen05 kernel, 1 = mma.sync kernel (VLO_ATTN=1 or G not dividing 128)
 struct AttnPlan {
   float* ws_o;
   float* ws_ml;

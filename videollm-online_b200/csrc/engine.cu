@@ -233,7 +233,7 @@ int vlo_engine_create(const vlo_config* cfg, int device, vlo_engine** out) {
   VLO_CHECK(c.num_heads % c.num_kv_heads == 0, "num_heads % num_kv_heads");
   VLO_CHECK(c.max_streams >= 1 && c.max_kv_tokens >= 64 && c.max_step_tokens >= 1, "capacities");
   VLO_CHECK(c.max_step_tokens <= 128, "max_step_tokens <= 128 (longer inputs are chunked by the host; chunked == one pass)");
-  VLO_CHECK(c.vit_layers == 0 || (c.vit_hidden % 64 == 0 && c.vit_hidden / c.vit_heads == 64 && c.vit_mlp % 64 == 0),
+  VLO_CHECK(c.vit_layers == 0 || (c.vit_hidden % 128 == 0 && c.vit_hidden / c.vit_heads == 64 && c.vit_mlp % 64 == 0),
             "vision tower: hidden % 64, head_dim == 64");
   VLO_CHECK(c.vit_layers == 0 || (c.image_size % c.patch_size == 0 && (3 * c.patch_size * c.patch_size) % 64 == 0 &&
                                   c.patch_size % 8 == 0),
@@ -533,38 +533,74 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
   CUtensorMap tm_qkv;
   if (tmap_2d_sw128(e->v_qkv, rows, 3 * C, kVitBlk, FMT_F16, &tm_qkv)) return -1;
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // head_dim 64
-  // out_proj / fc2 have few output tiles (N = C): split K so ~all SMs stream, then fuse the split-K fix-up,
-  // the fp32 residual add and the NEXT LayerNorm into one row kernel.
-  const int bn_c = 64;
-  const int tiles_c = ((rows + 127) / 128) * ((C + bn_c - 1) / bn_c);
-  auto pick_splits = [&](int k) {
-    int s = std::max(1, (2 * kNumSMs) / std::max(1, tiles_c));
-    s = std::min(s, std::max(1, (k / kGemmBK) / 4));
-    return gemm_fix_splits(k, std::min(s, 8));
+  // Trunk GEMMs on the persistent swap-AB kernel (weights ride MMA-M, the 576*B token rows are tiled along
+  // MMA-N): QKV and fc1 run whole tiles with the fused bias / GELU fp16 epilogue; out_proj and fc2 (few
+  // output tiles) run stream-K over all SMs and their partial planes are folded into the fp32 residual
+  // stream together with the NEXT LayerNorm by vit_fix_ln_kernel.
+  auto pick_bn = [&](int n_out, int mode) {
+    const int cands[4] = {64, 96, 128, 192};
+    int best = 64;
+    double best_eff = -1.0;
+    for (int bn : cands) {
+      const int xt = (rows + bn - 1) / bn;
+      const int tiles = ((n_out + 127) / 128) * xt;
+      double eff = static_cast<double>(rows) / (static_cast<double>(xt) * bn);          // padding waste
+      if (mode == 1) eff *= static_cast<double>(tiles) / (((tiles + kNumSMs - 1) / kNumSMs) * kNumSMs);  // wave quantisation
+      if (eff >= best_eff - 1e-9) {  // ties -> wider tile (better operand reuse)
+        best_eff = eff;
+        best = bn;
+      }
+    }
+    return best;
   };
-  VLO_CHECK(static_cast<size_t>(8) * rows * C <= e->v_part_elems, "ViT split-K workspace too small");
-  auto partial_gemm = [&](const __half* a, const __half* w, int k, int* splits) -> int {
-    GemmCall g{};
+  auto tiles_gemm = [&](const __half* x, const __half* w, int n_out, int k, __half* out, const float* bias, int act) -> int {
+    GemmWsCall g{};
     g.fmt = FMT_F16;
-    g.swap = 0;
-    g.epi = EPI_PARTIAL;
-    g.a = a;
-    g.rows_a = rows;
-    g.b = w;
-    g.rows_b = C;
+    g.mode = 1;
+    g.w = w;
+    g.rows_w = n_out;
+    g.x = x;
+    g.rows_x = rows;
+    g.k = k;
+    g.out = out;
+    g.ld_out = n_out;
+    g.bias = bias;
+    g.act = act;
+    g.bn = pick_bn(n_out, 1);
+    g.weights_hot = 1;
+    gemm_ws_plan(n_out, k, 1, 0, &g.sk, nullptr, (rows + g.bn - 1) / g.bn);
+    return gemm_ws_launch(g, st);
+  };
+  struct SkCall { SkInfo sk; int bn, xt; };
+  auto partial_gemm = [&](const __half* x, const __half* w, int k, SkCall* out) -> int {
+    GemmWsCall g{};
+    g.fmt = FMT_F16;
+    g.mode = 0;
+    g.w = w;
+    g.rows_w = C;
+    g.x = x;
+    g.rows_x = rows;
     g.k = k;
     g.out = e->v_part;
     g.ld_out = C;
-    g.splits = pick_splits(k);
-    g.split_stride = static_cast<long long>(rows) * C;
-    g.bn = bn_c;
-    *splits = g.splits;
-    return gemm_launch(g, st);
+    g.plane_stride = static_cast<long long>(rows) * C;
+    g.bn = pick_bn(C, 0);
+    g.weights_hot = 1;
+    int planes = 1;
+    out->bn = g.bn;
+    out->xt = (rows + g.bn - 1) / g.bn;
+    gemm_ws_plan(C, k, 0, 0, &g.sk, &planes, out->xt);
+    VLO_CHECK(planes <= 8 && static_cast<size_t>(planes) * rows * C <= e->v_part_elems, "ViT stream-K workspace too small");
+    out->sk = g.sk;
+    return gemm_ws_launch(g, st);
   };
-  auto fix_ln = [&](int splits, const float* bias, const float* lw, const float* lb, float* out32) -> int {
+  auto fix_ln = [&](const SkCall& sc, const float* bias, const float* lw, const float* lb, float* out32) -> int {
     VitFixLnParams p{};
     p.part = e->v_part;
-    p.n_splits = splits;
+    p.n_splits = -1;
+    p.sk = sc.sk;
+    p.sk_bn = sc.bn;
+    p.sk_xtiles = sc.xt;
     p.split_stride = static_cast<long long>(rows) * C;
     p.bias = bias;
     p.h = e->v_h;
@@ -584,24 +620,22 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
   count_launch();
   for (int l = 0; l < c.vit_layers; ++l) {
     const VitLayer& v = e->vit[l];
-    int S = 1;
-    if (gemm_store16(FMT_F16, 0, e->v_xn, rows, v.qkv_w, 3 * C, C, e->v_qkv, 3 * C, v.qkv_b, ACT_NONE, vit_bn(rows, 3 * C), st))
-      return -1;
+    SkCall sc{};
+    if (tiles_gemm(e->v_xn, v.qkv_w, 3 * C, C, e->v_qkv, v.qkv_b, ACT_NONE)) return -1;
     prof_begin(PROF_VIT_ATTN, st, 4.0 * rows * C * 2);
     vit_attn_kernel<<<dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), kVitThreads, kVitSmemBytes, st>>>(
         tm_qkv, e->v_attn, P, C, scale_log2);
     prof_end(st);
     VLO_LAUNCH_CHECK();
     count_launch();
-    if (partial_gemm(e->v_attn, v.out_w, C, &S)) return -1;
-    if (fix_ln(S, v.out_b, v.ln2_w, v.ln2_b, nullptr)) return -1;
-    if (gemm_store16(FMT_F16, 0, e->v_xn, rows, v.fc1_w, M, C, e->v_mlp, M, v.fc1_b, ACT_GELU_TANH, vit_bn(rows, M), st))
-      return -1;
-    if (partial_gemm(e->v_mlp, v.fc2_w, M, &S)) return -1;
+    if (partial_gemm(e->v_attn, v.out_w, C, &sc)) return -1;
+    if (fix_ln(sc, v.out_b, v.ln2_w, v.ln2_b, nullptr)) return -1;
+    if (tiles_gemm(e->v_xn, v.fc1_w, M, C, e->v_mlp, v.fc1_b, ACT_GELU_TANH)) return -1;
+    if (partial_gemm(e->v_mlp, v.fc2_w, M, &sc)) return -1;
     const bool last = (l == c.vit_layers - 1);
     // the LayerNorm that follows fc2: next block's layer_norm1, or post_layernorm (fp16 copy feeds the MAP
     // head, fp32 copy feeds the pool)
-    if (fix_ln(S, v.fc2_b, last ? e->post_ln_w : e->vit[l + 1].ln1_w, last ? e->post_ln_b : e->vit[l + 1].ln1_b,
+    if (fix_ln(sc, v.fc2_b, last ? e->post_ln_w : e->vit[l + 1].ln1_w, last ? e->post_ln_b : e->vit[l + 1].ln1_b,
                last ? e->v_ln32 : nullptr))
       return -1;
   }

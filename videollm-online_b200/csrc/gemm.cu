@@ -217,7 +217,8 @@ int launch_ws(const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsArgs& a,
   }
   if (prof_on()) {
     const double out_b = a.mode == 0 ? 4.0 * a.rows_x * a.rows_w : 2.0 * a.rows_x * a.rows_w;
-    prof_begin(PROF_GEMM_STREAM, stream, 2.0 * a.k * (static_cast<double>(a.rows_w) + a.rows_x) + out_b);
+    prof_begin(FMT == FMT_BF16 ? PROF_GEMM_STREAM : PROF_GEMM_VIT, stream,
+               2.0 * a.k * (static_cast<double>(a.rows_w) + a.rows_x) + out_b);
   }
   VLO_CUDA(launch_pdl(kern, dim3(a.sk.G), dim3(kGemmThreads), GemmWsCfg<BN>::kSmemBytes, stream, tw, tx, a));
   prof_end(stream);
@@ -226,8 +227,8 @@ int launch_ws(const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsArgs& a,
 }
 }  // namespace
 
-int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_planes) {
-  const int tiles = (rows_w + kGemmBM - 1) / kGemmBM;
+int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_planes, int x_tiles) {
+  const int tiles = ((rows_w + kGemmBM - 1) / kGemmBM) * (x_tiles > 0 ? x_tiles : 1);
   const int kb = k / kGemmBK;
   sk->kb = kb;
   sk->U = static_cast<long long>(tiles) * kb;
@@ -244,13 +245,18 @@ int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_p
 
 int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream) {
   VLO_CHECK(c.k > 0 && c.k % kGemmBK == 0, "K must be a positive multiple of 64");
-  VLO_CHECK(c.rows_w > 0 && c.rows_x > 0 && c.rows_x <= 128, "weight-streaming GEMM handles 1..128 token rows");
-  const int bn = c.rows_x <= 16 ? 16 : (c.rows_x <= 32 ? 32 : (c.rows_x <= 64 ? 64 : 128));
+  VLO_CHECK(c.rows_w > 0 && c.rows_x > 0, "empty GEMM operand");
+  const int bn = c.bn > 0 ? c.bn : (c.rows_x <= 16 ? 16 : (c.rows_x <= 32 ? 32 : (c.rows_x <= 64 ? 64 : 128)));
+  const int x_tiles = (c.rows_x + bn - 1) / bn;
+  VLO_CHECK(c.sk.U == static_cast<long long>((c.rows_w + kGemmBM - 1) / kGemmBM) * x_tiles * (c.k / kGemmBK),
+            "gemm_ws: plan does not match the call (x_tiles / bn)");
   GemmWsArgs a{};
   a.rows_w = c.rows_w;
   a.rows_x = c.rows_x;
   a.k = c.k;
-  a.tiles = (c.rows_w + kGemmBM - 1) / kGemmBM;
+  a.tiles = ((c.rows_w + kGemmBM - 1) / kGemmBM) * x_tiles;
+  a.x_tiles = x_tiles;
+  a.hint_w = c.weights_hot ? kEvictNormal : kEvictFirst;
   a.sk = c.sk;
   a.mode = c.mode;
   a.out = c.out;
@@ -271,6 +277,8 @@ int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream) {
   VLO_WS_CASE(FMT_F16, 32)
   VLO_WS_CASE(FMT_F16, 64)
   VLO_WS_CASE(FMT_F16, 128)
+  VLO_WS_CASE(FMT_F16, 96)
+  VLO_WS_CASE(FMT_F16, 192)
 #undef VLO_WS_CASE
   return fail("gemm_ws_launch: no kernel instance");
 }

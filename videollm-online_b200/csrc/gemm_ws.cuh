@@ -20,7 +20,8 @@ namespace vlo {
 
 struct GemmWsArgs {
   int rows_w, rows_x, k;   // W [rows_w, k], X [rows_x, k]
-  int tiles;               // ceil(rows_w / 128)
+  int tiles;               // weight tiles x token tiles
+  int x_tiles;             // ceil(rows_x / BN) token tiles (1 for the decoder); tile = w_tile * x_tiles + x_tile
   SkInfo sk;
   int mode;                // 0 = stream-K partials, 1 = whole tiles + 16-bit epilogue
   void* out;               // mode 0: fp32 [plane][rows_x][rows_w]; mode 1: 16-bit [rows_x][ld_out]
@@ -28,14 +29,15 @@ struct GemmWsArgs {
   long long plane_stride;
   const float* bias;
   int act;
+  unsigned long long hint_w;  // L2 policy for the weight stream (evict-first when read once per launch)
 };
 
 template <int BN>
 struct GemmWsCfg {
-  static constexpr int kStages = BN <= 64 ? 8 : 6;
+  static constexpr int kStages = BN <= 64 ? 8 : (BN <= 96 ? 7 : (BN <= 128 ? 6 : 5));
   static constexpr int kBytesA = kGemmBM * kGemmBK * 2;
   static constexpr int kBytesB = BN * kGemmBK * 2;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * (kBytesA + kBytesB) + 1024 + 256;
 };
 
@@ -97,12 +99,13 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       for (long long u = u0; u < u1; ++u, ++i) {
         const int tile = static_cast<int>(u / kb);
         const int kblk = static_cast<int>(u - static_cast<long long>(tile) * kb);
+        const int wt = tile / p.x_tiles, xt = tile - wt * p.x_tiles;
         const int s = i % S;
         const uint32_t ph = (i / S) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], Cfg::kBytesA + Cfg::kBytesB);
-        tma_load_2d(smem_a + s * Cfg::kBytesA, &tm_w, &full_bar[s], kblk * kGemmBK, tile * kGemmBM, kEvictFirst);
-        tma_load_2d(smem_b + s * Cfg::kBytesB, &tm_x, &full_bar[s], kblk * kGemmBK, 0, kEvictLast);
+        tma_load_2d(smem_a + s * Cfg::kBytesA, &tm_w, &full_bar[s], kblk * kGemmBK, wt * kGemmBM, p.hint_w);
+        tma_load_2d(smem_b + s * Cfg::kBytesB, &tm_x, &full_bar[s], kblk * kGemmBK, xt * BN, kEvictLast);
       }
     }
   } else if (warp == 1) {
@@ -146,7 +149,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       const int buf = item & 1;
       mbar_wait(&acc_full[buf], (item >> 1) & 1);
       tc_fence_after();
-      const int n = tile * kGemmBM + q * 32 + lane;  // output feature (row of W)
+      const int wt = tile / p.x_tiles, xt = tile - wt * p.x_tiles;
+      const int n = wt * kGemmBM + q * 32 + lane;  // output feature (row of W)
+      const int t0 = xt * BN;                      // first token row of this tile
       const bool n_ok = n < p.rows_w;
       float* plane = nullptr;
       float bias_n = 0.f;
@@ -167,10 +172,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (!n_ok || c0 >= p.rows_x) continue;
+        if (!n_ok || t0 + c0 >= p.rows_x) continue;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int t = c0 + j;
+          const int t = t0 + c0 + j;
           if (t >= p.rows_x) break;
           const float acc = __uint_as_float(v[j]);
           if (p.mode == 0) {

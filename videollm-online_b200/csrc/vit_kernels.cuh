@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include "mma.cuh"
 #include "ptx.cuh"
+#include "streamk.h"
 
 namespace vlo {
 
@@ -85,8 +86,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const InT* in, const flo
 //   h[r] += y                                     (fp32 residual stream, HF:...siglip.py:353,360)
 //   out  = LayerNorm(h[r])                        (the next layer_norm1 / layer_norm2 / post_layernorm)
 struct VitFixLnParams {
-  const float* part;  // [n_splits][rows][C]
-  int n_splits;
+  const float* part;  // [planes][rows][C]
+  int n_splits;       // > 0: that many planes; < 0: stream-K planes of tile (col/128) * sk_xtiles + row / sk_bn
+  SkInfo sk;
+  int sk_bn, sk_xtiles;
   long long split_stride;
   const float* bias;
   float* h;
@@ -98,18 +101,35 @@ struct VitFixLnParams {
   float eps;
 };
 __global__ void __launch_bounds__(256) vit_fix_ln_kernel(const VitFixLnParams p) {
+  // 4 contiguous channels per thread per sweep; the (<= 8) plane loads of a sweep are independent.
   extern __shared__ float row[];
   __shared__ float red[32];
   const size_t r = blockIdx.x;
   const int C = p.C;
   float s = 0.f;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    float y = 0.f;
-    for (int k = 0; k < p.n_splits; ++k) y += p.part[k * p.split_stride + r * C + i];
-    const float v = p.h[r * C + i] + fp16_round(y + p.bias[i]);
-    p.h[r * C + i] = v;
-    row[i] = v;
-    s += v;
+  for (int i = threadIdx.x * 4; i < C; i += blockDim.x * 4) {
+    float4 a[8];
+    const int ns = p.n_splits > 0 ? p.n_splits
+                                  : sk_planes((i >> 7) * p.sk_xtiles + static_cast<int>(r) / p.sk_bn, p.sk);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      a[k] = (k < ns) ? *reinterpret_cast<const float4*>(p.part + k * p.split_stride + r * C + i)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 hv = *reinterpret_cast<const float4*>(p.h + r * C + i);
+    const float4 bv = *reinterpret_cast<const float4*>(p.bias + i);
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      y.x += a[k].x; y.y += a[k].y; y.z += a[k].z; y.w += a[k].w;
+    }
+    float4 v;
+    v.x = hv.x + fp16_round(y.x + bv.x);
+    v.y = hv.y + fp16_round(y.y + bv.y);
+    v.z = hv.z + fp16_round(y.z + bv.z);
+    v.w = hv.w + fp16_round(y.w + bv.w);
+    *reinterpret_cast<float4*>(p.h + r * C + i) = v;
+    *reinterpret_cast<float4*>(row + i) = v;
+    s += v.x + v.y + v.z + v.w;
   }
   s = warp_sum(s);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -120,9 +140,10 @@ __global__ void __launch_bounds__(256) vit_fix_ln_kernel(const VitFixLnParams p)
   const float mean = tot / C;
   __syncthreads();
   float q = 0.f;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    const float d = row[i] - mean;
-    q += d * d;
+  for (int i = threadIdx.x * 4; i < C; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
   }
   q = warp_sum(q);
   if (lane == 0) red[warp] = q;
@@ -130,10 +151,23 @@ __global__ void __launch_bounds__(256) vit_fix_ln_kernel(const VitFixLnParams p)
   float var = 0.f;
   for (int i = 0; i < nw; ++i) var += red[i];
   const float rstd = rsqrtf(var / C + p.eps);
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    const float y = (row[i] - mean) * rstd * p.ln_w[i] + p.ln_b[i];
-    if (p.out16) p.out16[r * C + i] = __float2half_rn(y);
-    if (p.out32) p.out32[r * C + i] = y;
+  for (int i = threadIdx.x * 4; i < C; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    const float4 w = *reinterpret_cast<const float4*>(p.ln_w + i);
+    const float4 b = *reinterpret_cast<const float4*>(p.ln_b + i);
+    float4 y;
+    y.x = (v.x - mean) * rstd * w.x + b.x;
+    y.y = (v.y - mean) * rstd * w.y + b.y;
+    y.z = (v.z - mean) * rstd * w.z + b.z;
+    y.w = (v.w - mean) * rstd * w.w + b.w;
+    if (p.out16) {
+      __half2 h01 = __floats2half2_rn(y.x, y.y), h23 = __floats2half2_rn(y.z, y.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&h01);
+      o.y = *reinterpret_cast<uint32_t*>(&h23);
+      *reinterpret_cast<uint2*>(p.out16 + r * C + i) = o;
+    }
+    if (p.out32) *reinterpret_cast<float4*>(p.out32 + r * C + i) = y;
   }
 }
 
