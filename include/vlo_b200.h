@@ -161,6 +161,9 @@ int vlo_op_gemm_ws(int fmt, int mode, const void* d_w, int rows_w, const void* d
 /* which generation of the KV-append attention kernel runs for this head layout: 2 = tcgen05 (csrc/attn_tc.cuh),
  * 1 = mma.sync (csrc/attn.cuh; forced by VLO_ATTN=1, or when n_heads/n_kv_heads does not divide 128) */
 int vlo_op_attn_version(int n_heads, int n_kv_heads);
+/* developer aid: with VLO_ATTN_TRACE=1 the tcgen05 attention kernel records clock64 stamps per CTA and role
+ * ([cta][3 roles][64]); this copies the first n values to the host (tools/gpu_attn_trace.py). */
+int vlo_debug_attn_trace(long long* h_out, int n);
 int64_t vlo_op_attn_ws_bytes(int n_tok, int n_heads, int head_dim, int kv_len);
 int vlo_op_attn_kvappend(const void* d_q, const void* d_k, const void* d_v, void* d_out, float* d_ws, int n_tok,
                          int n_heads, int n_kv_heads, int head_dim, int kv_len, long long kv_stride, void* cuda_stream);

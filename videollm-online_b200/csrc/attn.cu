@@ -128,6 +128,9 @@ int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, in
   return 0;
 }
 
+static long long* g_attn_trace = nullptr;
+long long* attn_trace_buffer() { return g_attn_trace; }
+
 static int launch_merge(const AttnPlan& plan, void* d_out, int n_heads, int n_kv_heads, float scale_log2, cudaStream_t stream) {
   AttnMergeParams mp{};
   mp.ws_o = plan.ws_o;
@@ -169,6 +172,20 @@ static int attn_run_tc(const AttnPlan& plan, const void* d_q, const void* d_k, c
   if (swap_ls < 0) {
     const char* e = getenv("VLO_ATTN_VDESC");
     swap_ls = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  {  // VLO_ATTN_TRACE=1: per-CTA clock64 timeline into a device buffer dumped by tools/gpu_attn_trace.py
+    static long long* dbg = nullptr;
+    static int want = -1;
+    if (want < 0) {
+      const char* e = getenv("VLO_ATTN_TRACE");
+      want = (e != nullptr && e[0] == '1') ? 1 : 0;
+      if (want) {
+        cudaMalloc(&dbg, sizeof(long long) * 192 * 4096);
+        cudaMemset(dbg, 0, sizeof(long long) * 192 * 4096);
+      }
+    }
+    p.dbg = dbg;
+    g_attn_trace = dbg;
   }
   p.v_lbo = swap_ls ? 1024u : static_cast<uint32_t>(kTcSub);
   p.v_sbo = swap_ls ? static_cast<uint32_t>(kTcSub) : 1024u;

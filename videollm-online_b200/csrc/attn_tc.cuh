@@ -72,10 +72,23 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int b_mn_ma
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {  // one MUFU.EX2; inputs here are <= 8, underflow flushes to 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnTcParams {
   AttnParams base;
   uint32_t v_lbo, v_sbo;  // V descriptor strides (bytes)
+  long long* dbg;         // optional timeline buffer (VLO_ATTN_TRACE): [cta][role][64] clock64 stamps
 };
+#define VLO_TC_STAMP(role, idx)                                                                          \
+  do {                                                                                                   \
+    if (pp.dbg != nullptr && (idx) < 64)                                                                 \
+      pp.dbg[((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 192 + \
+             (role) * 64 + (idx)] = clock64();                                                           \
+  } while (0)
 
 // swizzled byte offset of 16-byte chunk `c16` (0..15 along the 128-element row) of row `r` in a
 // [2 sub-tiles][128 rows][128 B] K-major tile
@@ -106,6 +119,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) VLO_TC_STAMP(0, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
@@ -130,9 +144,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-  pdl_trigger();
 
+  // Work item and split geometry.  The item table was uploaded at the start of the step, i.e. by an operation
+  // older than our immediate predecessor kernel, so it may be read before pdl_wait() (every kernel of the
+  // step triggers only after its own wait; see ptx.cuh).
   const AttnItem it = p.items[blockIdx.z];
   const int split = blockIdx.x;
   const int kvh = blockIdx.y;
@@ -143,22 +158,46 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   const int blk0 = split * it.blocks_per_split;
   const int nblk = (split < it.n_splits) ? min(blk0 + it.blocks_per_split, nblk_total) - blk0 : 0;
   const uint32_t tS = tmem_base, tO = tmem_base + 256;
+  const int row_base = it.kv_row0 + kvh * it.kv_head_stride;
+
+  // K/V rows of EARLIER steps do not depend on the predecessor either (only the rows appended in this step
+  // do): prefetch the first blocks that end safely below this step's new tokens before waiting.
+  int pre = 0;
+  if (warp == 0 && lane == 0) {
+    const int safe_end = it.q_pos0 - 128;  // a step appends at most 128 tokens per stream
+    for (; pre < nblk && pre < kTcStages; ++pre) {
+      if ((blk0 + pre) * kTcBlk + kTcBlk - 1 >= safe_end) break;
+      uint8_t* st = kv_tile + pre * kTcStageBytes;
+      const int row = row_base + (blk0 + pre) * kTcBlk;
+      mbar_arrive_expect_tx(&k_full[pre], kTcHalf);
+      tma_load_2d(st, &tm_k, &k_full[pre], 0, row, kEvictFirst);
+      tma_load_2d(st + kTcSub, &tm_k, &k_full[pre], 64, row, kEvictFirst);
+      mbar_arrive_expect_tx(&v_full[pre], kTcHalf);
+      tma_load_2d(st + 2 * kTcSub, &tm_v, &v_full[pre], 0, row, kEvictFirst);
+      tma_load_2d(st + 3 * kTcSub, &tm_v, &v_full[pre], 64, row, kEvictFirst);
+    }
+  }
+  if (threadIdx.x == 0) VLO_TC_STAMP(0, 1);
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0) VLO_TC_STAMP(0, 2);
 
   if (nblk > 0) {
     if (warp == 0) {
       if (lane == 0) {
         // ------------------------------------------------------------ TMA producer
-        const int row_base = it.kv_row0 + kvh * it.kv_head_stride;
-        for (int j = 0; j < nblk; ++j) {
+        for (int j = pre; j < nblk; ++j) {
           const int s = j % kTcStages;
           const uint32_t ph = (j / kTcStages) & 1;
           uint8_t* st = kv_tile + s * kTcStageBytes;
           const int row = row_base + (blk0 + j) * kTcBlk;
           mbar_wait(&k_empty[s], ph ^ 1);
+          VLO_TC_STAMP(0, 4 + 2 * j);
           mbar_arrive_expect_tx(&k_full[s], kTcHalf);
           tma_load_2d(st, &tm_k, &k_full[s], 0, row, kEvictFirst);
           tma_load_2d(st + kTcSub, &tm_k, &k_full[s], 64, row, kEvictFirst);
           mbar_wait(&v_empty[s], ph ^ 1);
+          VLO_TC_STAMP(0, 5 + 2 * j);
           mbar_arrive_expect_tx(&v_full[s], kTcHalf);
           tma_load_2d(st + 2 * kTcSub, &tm_v, &v_full[s], 0, row, kEvictFirst);
           tma_load_2d(st + 3 * kTcSub, &tm_v, &v_full[s], 64, row, kEvictFirst);
@@ -178,6 +217,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
           mbar_wait(&v_full[s], (i / kTcStages) & 1);
           mbar_wait(&p_full[b], (i >> 1) & 1);
           tc_fence_after();
+          VLO_TC_STAMP(1, 3 * i + 2);
           const uint32_t p_addr = smem_u32(p_tile + b * kTcPBytes);
           const uint32_t v_addr = smem_u32(kv_tile + s * kTcStageBytes + 2 * kTcSub);
 #pragma unroll
@@ -194,8 +234,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
           const int s = j % kTcStages;
           const int b = j & 1;
           mbar_wait(&k_full[s], (j / kTcStages) & 1);
+          VLO_TC_STAMP(1, 3 * j);
           mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
           tc_fence_after();
+          VLO_TC_STAMP(1, 3 * j + 1);
           const uint32_t k_addr = smem_u32(kv_tile + s * kTcStageBytes);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {  // 16 dims per MMA
@@ -229,6 +271,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         }
         fence_proxy_async();
         mbar_arrive(q_ready);
+        if (r == 0) VLO_TC_STAMP(2, 0);
       }
       const float c = p.scale_log2;
       float m_ref = -INFINITY, l_run = 0.f;
@@ -236,6 +279,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         const int b = j & 1;
         mbar_wait(&s_full[b], (j >> 1) & 1);
         tc_fence_after();
+        if (r == 0) VLO_TC_STAMP(2, 4 + 4 * j);
         const int key0 = (blk0 + j) * kTcBlk;
         const bool need_mask = key0 + kTcBlk - 1 > it.q_pos0;  // block reaches past the first query's limit
         // S row -> registers (128 fp32), masked, row max
@@ -250,6 +294,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         }
         tc_fence_before();
         mbar_arrive(&s_empty[b]);   // S[b] may be overwritten by block j+2
+        if (r == 0) VLO_TC_STAMP(2, 5 + 4 * j);
         if (need_mask) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
@@ -258,9 +303,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 128; ++i) sv[i] = -INFINITY;
         }
-        float mx = -INFINITY;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, sv[i]);
+        for (int i = 0; i < 128; i += 4) {
+          mx4[0] = fmaxf(mx4[0], sv[i]);
+          mx4[1] = fmaxf(mx4[1], sv[i + 1]);
+          mx4[2] = fmaxf(mx4[2], sv[i + 2]);
+          mx4[3] = fmaxf(mx4[3], sv[i + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // lazy rescale: keep the old reference max unless the new one is much larger
         const float m_new = fmaxf(m_ref, mx);
         const bool grow = (m_ref == -INFINITY) ? (m_new != -INFINITY) : ((m_new - m_ref) * c > kTcRescaleLog2);
@@ -287,26 +338,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         const float moff = (m_ref == -INFINITY) ? 0.f : m_ref * c;
         // P = exp2(S c - m c) -> bf16 -> swizzled smem tile; wait for the P buffer to be free first
         mbar_wait(&p_empty[b], ((j >> 1) & 1) ^ 1);
+        if (r == 0) VLO_TC_STAMP(2, 6 + 4 * j);
         uint8_t* pt = p_tile + b * kTcPBytes;
-        float ps = 0.f;
+        float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float nmoff = -moff;
 #pragma unroll
         for (int c16 = 0; c16 < 16; ++c16) {
           uint32_t w[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float p0 = exp2f(sv[c16 * 8 + 2 * k] * c - moff), p1 = exp2f(sv[c16 * 8 + 2 * k + 1] * c - moff);
-            ps += p0 + p1;
+            const float p0 = ex2_approx(fmaf(sv[c16 * 8 + 2 * k], c, nmoff));
+            const float p1 = ex2_approx(fmaf(sv[c16 * 8 + 2 * k + 1], c, nmoff));
+            ps4[k] += p0 + p1;
             w[k] = pack_bf16(p0, p1);
           }
           *reinterpret_cast<uint4*>(pt + tc_sw_off(r, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        const float ps = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
         l_run += ps;
         fence_proxy_async();        // make the generic-proxy P writes visible to the MMA (async proxy)
         mbar_arrive(&p_full[b]);
+        if (r == 0) VLO_TC_STAMP(2, 7 + 4 * j);
       }
       // ---- epilogue: partial (m, l, O) of this split; merged by attn_merge_kernel
       mbar_wait(o_done, (nblk - 1) & 1);
       tc_fence_after();
+      if (r == 0) VLO_TC_STAMP(2, 1);
       const int rows = it.q_count * G;
       const int rr = t * G + g;  // row index inside the item, same convention as v1 / the merge kernel
       const size_t slot = static_cast<size_t>(it.ws_slot0) + (static_cast<size_t>(kvh) * it.n_splits + split) * rows + rr;
@@ -327,6 +384,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         p.ws_ml[slot * 2] = m_ref;
         p.ws_ml[slot * 2 + 1] = l_run;
       }
+      if (r == 0) VLO_TC_STAMP(2, 2);
       tc_fence_before();
     }
   }

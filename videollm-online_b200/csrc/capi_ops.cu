@@ -86,6 +86,14 @@ int vlo_op_gemm_ws(int fmt, int mode, const void* d_w, int rows_w, const void* d
   return gemm_ws_launch(c, static_cast<cudaStream_t>(cuda_stream));
 }
 
+/* debug: copy the VLO_ATTN_TRACE timeline (n int64 values) to the host; returns -1 when tracing is off */
+int vlo_debug_attn_trace(long long* h_out, int n) {
+  long long* d = attn_trace_buffer();
+  if (d == nullptr) return fail("attention tracing is off (set VLO_ATTN_TRACE=1)");
+  VLO_CUDA(cudaMemcpy(h_out, d, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int vlo_op_attn_version(int n_heads, int n_kv_heads) { return attn_version(n_heads, n_kv_heads); }
 
 int64_t vlo_op_attn_ws_bytes(int n_tok, int n_heads, int head_dim, int kv_len) {

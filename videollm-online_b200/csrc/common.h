@@ -130,7 +130,8 @@ struct AttnSeq {
 // bytes of scratch attn_launch needs for these sequences (upper bound)
 size_t attn_ws_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads);
 size_t attn_stage_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads);
-int attn_version(int n_heads, int n_kv_heads);  // 2 = tcgen05 kernel, 1 = mma.sync kernel (VLO_ATTN=1 or G not dividing 128)
+int attn_version(int n_heads, int n_kv_heads);
+long long* attn_trace_buffer();  // device buffer of the VLO_ATTN_TRACE timeline (nullptr when off)  // 2 = tcgen05 kernel, 1 = mma.sync kernel (VLO_ATTN=1 or G not dividing 128)
 struct AttnPlan {
   float* ws_o;
   float* ws_ml;

@@ -503,9 +503,8 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
   // K1/K2: normalise + patchify, then patch-embed GEMM with bias + position embedding epilogue
   {
     const long long total = static_cast<long long>(rows) * e->patch_k / 8;
-    patchify_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 4096)), 256, 0, st>>>(
-        d_frames, e->patches, B, c.image_size, c.patch_size);
-    VLO_LAUNCH_CHECK();
+    VLO_CUDA(launch_pdl(patchify_kernel, dim3(static_cast<unsigned>(std::min<long long>((total + 255) / 256, 4096))), dim3(256), 0, st,
+                        d_frames, e->patches, B, c.image_size, c.patch_size));
     count_launch();
     GemmCall g{};
     g.fmt = FMT_F16;
@@ -610,23 +609,21 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     p.out32 = out32;
     p.C = C;
     p.eps = c.vit_ln_eps;
-    vit_fix_ln_kernel<<<rows, 256, ln_smem, st>>>(p);
-    VLO_LAUNCH_CHECK();
+    VLO_CUDA(launch_pdl(vit_fix_ln_kernel, dim3(rows), dim3(256), ln_smem, st, p));
     count_launch();
     return 0;
   };
-  layernorm_kernel<float><<<rows, 256, ln_smem, st>>>(e->v_h, e->vit[0].ln1_w, e->vit[0].ln1_b, e->v_xn, nullptr, C, c.vit_ln_eps);
-  VLO_LAUNCH_CHECK();
+  VLO_CUDA(launch_pdl(layernorm_kernel<float>, dim3(rows), dim3(256), ln_smem, st, static_cast<const float*>(e->v_h),
+                      e->vit[0].ln1_w, e->vit[0].ln1_b, e->v_xn, static_cast<float*>(nullptr), C, c.vit_ln_eps));
   count_launch();
   for (int l = 0; l < c.vit_layers; ++l) {
     const VitLayer& v = e->vit[l];
     SkCall sc{};
     if (tiles_gemm(e->v_xn, v.qkv_w, 3 * C, C, e->v_qkv, v.qkv_b, ACT_NONE)) return -1;
     prof_begin(PROF_VIT_ATTN, st, 4.0 * rows * C * 2);
-    vit_attn_kernel<<<dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), kVitThreads, kVitSmemBytes, st>>>(
-        tm_qkv, e->v_attn, P, C, scale_log2);
+    VLO_CUDA(launch_pdl(vit_attn_kernel, dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), dim3(kVitThreads), kVitSmemBytes, st,
+                        tm_qkv, e->v_attn, P, C, scale_log2));
     prof_end(st);
-    VLO_LAUNCH_CHECK();
     count_launch();
     if (partial_gemm(e->v_attn, v.out_w, C, &sc)) return -1;
     if (fix_ln(sc, v.out_b, v.ln2_w, v.ln2_b, nullptr)) return -1;

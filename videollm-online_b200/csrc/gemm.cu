@@ -102,9 +102,8 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& arg
                          esz * static_cast<double>(args.rows_a) * args.rows_b * (EPI == EPI_PARTIAL ? grid.z : 1);
     prof_begin(SWAP ? PROF_GEMM_STREAM : PROF_GEMM_VIT, stream, bytes);
   }
-  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, args);
+  VLO_CUDA(launch_pdl(kern, grid, dim3(kGemmThreads), GemmCfg<BN>::kSmemBytes, stream, ta, tb, args));
   prof_end(stream);
-  VLO_LAUNCH_CHECK();
   count_launch();
   return 0;
 }

@@ -88,7 +88,19 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // everything above overlapped the previous kernel's tail; its results are needed from here on
+  // The weight operand never depends on the predecessor kernel: the producer starts streaming the first
+  // S weight k-blocks right away, i.e. while the previous (small fix-up) kernel is still running.
+  int pre = 0;
+  if (warp == 0 && lane == 0) {
+    for (long long u = u0; u < u1 && pre < S; ++u, ++pre) {
+      const int tile = static_cast<int>(u / kb);
+      const int kblk = static_cast<int>(u - static_cast<long long>(tile) * kb);
+      const int wt = tile / p.x_tiles;
+      mbar_arrive_expect_tx(&full_bar[pre], Cfg::kBytesA + Cfg::kBytesB);
+      tma_load_2d(smem_a + pre * Cfg::kBytesA, &tm_w, &full_bar[pre], kblk * kGemmBK, wt * kGemmBM, p.hint_w);
+    }
+  }
+  // everything above overlapped the previous kernel's tail; its results (the activations) are needed from here on
   pdl_wait();
   pdl_trigger();
 
@@ -101,10 +113,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         const int kblk = static_cast<int>(u - static_cast<long long>(tile) * kb);
         const int wt = tile / p.x_tiles, xt = tile - wt * p.x_tiles;
         const int s = i % S;
-        const uint32_t ph = (i / S) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::kBytesA + Cfg::kBytesB);
-        tma_load_2d(smem_a + s * Cfg::kBytesA, &tm_w, &full_bar[s], kblk * kGemmBK, wt * kGemmBM, p.hint_w);
+        if (i >= pre) {
+          const uint32_t ph = (i / S) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kBytesA + Cfg::kBytesB);
+          tma_load_2d(smem_a + s * Cfg::kBytesA, &tm_w, &full_bar[s], kblk * kGemmBK, wt * kGemmBM, p.hint_w);
+        }
         tma_load_2d(smem_b + s * Cfg::kBytesB, &tm_x, &full_bar[s], kblk * kGemmBK, xt * BN, kEvictLast);
       }
     }
