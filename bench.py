@@ -171,7 +171,7 @@ def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 4, vit_laye
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     import torch
     t0 = time.perf_counter()
     per_step, info = cpu_reference_times(max(1, args.steps), max(0, args.warmup))
@@ -185,7 +185,7 @@ def run_reference_arm(args):
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -212,7 +212,8 @@ def run_engine_arm(args):
     K, Wm = args.steps, max(3, args.warmup)
     n_frames = K + Wm + 8
     cap = ((KV_START + 11 * (2 * n_frames + 8) + 63) // 64) * 64 + 128
-    eng = Engine(cfg, dev, max_streams=1, max_kv_tokens=cap, max_step_tokens=32, max_vit_batch=1)
+    n_extra = 8 if (world == 1 and args.extras) else 1   # streams for the config-3 side measurement
+    eng = Engine(cfg, dev, max_streams=n_extra, max_kv_tokens=cap, max_step_tokens=128, max_vit_batch=n_extra)
 
     # ---- weights: rank 0 synthesises, everyone else receives them over NCCL/NVLink (init only)
     from videollm_online_b200.dist import broadcast_weights
@@ -305,6 +306,26 @@ def run_engine_arm(args):
         eng.lib.vlo_profile_read(ms, n, by, ncls)
         eng.lib.vlo_profile_enable(0)
         hbm_peak, tf_peak, which = _peaks()
+        # kernel-class micro loops: one event pair around many back-to-back launches on the real buffers
+        def micro(fn, iters):
+            fn(1)
+            torch.cuda.synchronize()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record(stream); fn(iters); m1.record(stream)
+            torch.cuda.synchronize()
+            return m0.elapsed_time(m1) / iters
+        ab, gb, gl = C.c_double(0), C.c_double(0), C.c_int(0)
+        def run_attn(it):
+            rc = eng.lib.vlo_bench_attn(eng._h, sid, 11, it, C.byref(ab), eng._stream()); assert rc == 0, eng.lib.vlo_last_error()
+        def run_gemm(it):
+            rc = eng.lib.vlo_bench_gemm(eng._h, 11, it, C.byref(gb), C.byref(gl), eng._stream()); assert rc == 0, eng.lib.vlo_last_error()
+        eng.kv_truncate(sid, KV_START + 11)
+        attn_ms = micro(run_attn, 4) / cfg.num_hidden_layers          # per launch pair (main kernel + merge)
+        gemm_ms_iter = micro(run_gemm, 4)
+        micro_attn = {"us_per_launch_incl_merge": attn_ms * 1e3, "algo_bytes_per_launch": ab.value,
+                      "achieved_gbs": ab.value / 1e9 / (attn_ms / 1e3)}
+        micro_gemm = {"us_per_launch": gemm_ms_iter * 1e3 / gl.value, "algo_bytes_per_launch": gb.value / gl.value,
+                      "achieved_gbs": gb.value / 1e9 / (gemm_ms_iter / 1e3), "launches": gl.value}
         names = ["gemm_weight_stream", "attn_kvappend", "attn_merge", "gemm_vit", "vit_attn", "other"]
         cls = {}
         for j, nm in enumerate(names):
@@ -312,23 +333,73 @@ def run_engine_arm(args):
                 cls[nm] = {"launches_per_step": n[j] / P, "ms_per_step": ms[j] / P, "avg_us_per_launch": 1e3 * ms[j] / n[j],
                            "algo_gb_per_step": by[j] / P / 1e9, "achieved_gbs": (by[j] / 1e9) / (ms[j] / 1e3) if ms[j] > 0 else None}
         gs, at = cls.get("gemm_weight_stream"), cls.get("attn_kvappend")
-        roof = {"bound": "hbm", "kernel": "gemm_tn_kernel<bf16, swap-AB> (decoder weight streaming: 15.0 GB of the 16.6 GB/step)",
-                "achieved": gs["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": gs["achieved_gbs"] / hbm_peak,
+        roof = {"bound": "hbm", "kernel": "gemm_ws_kernel<bf16> (persistent stream-K weight streaming: 14.0 GB of the 16.6 GB/step)",
+                "achieved": micro_gemm["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": micro_gemm["achieved_gbs"] / hbm_peak,
                 "peak_source": which, "traffic": None,
-                "avg_us_per_launch": gs["avg_us_per_launch"], "launches_per_step": gs["launches_per_step"],
-                "algo_bytes_per_launch": 1e9 * gs["algo_gb_per_step"] / gs["launches_per_step"]}
-        roof_attn = {"bound": "hbm", "kernel": "attn_kvappend_kernel (KV-append attention, one launch per layer)",
-                     "achieved": at["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": at["achieved_gbs"] / hbm_peak,
-                     "peak_source": which, "traffic": None, "avg_us_per_launch": at["avg_us_per_launch"],
-                     "algo_bytes_per_launch": 1e9 * at["algo_gb_per_step"] / at["launches_per_step"]}
+                "avg_us_per_launch": micro_gemm["us_per_launch"], "algo_bytes_per_launch": micro_gemm["algo_bytes_per_launch"],
+                "method": "CUDA events around 4 back-to-back passes of the 128 decoder GEMM launches (q|k|v, o, gate|up, down of all 32 layers) on the engine's buffers, T=11",
+                "in_step_event_bracketed": {"achieved": gs["achieved_gbs"], "avg_us_per_launch": gs["avg_us_per_launch"],
+                                            "note": "per-launch event pairs inside the step (PDL off): includes ~3-5 us bracket overhead per launch"}}
+        roof_attn = {"bound": "hbm", "kernel": "attn_tc_kernel + attn_merge_kernel (KV-append attention, tcgen05; one launch pair per layer)",
+                     "achieved": micro_attn["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": micro_attn["achieved_gbs"] / hbm_peak,
+                     "peak_source": which, "traffic": None, "avg_us_per_launch": micro_attn["us_per_launch_incl_merge"],
+                     "algo_bytes_per_launch": micro_attn["algo_bytes_per_launch"],
+                     "method": "CUDA events around 4x32 back-to-back launch pairs over the 32 layers' caches (1.6 GB, > L2), q=11, kv=12011; merge kernel time included",
+                     "in_step_event_bracketed": {"achieved": at["achieved_gbs"], "avg_us_per_launch": at["avg_us_per_launch"]}}
         step_bytes = 15009316864 + (KV_START + 11 * (K // 2)) * 131072
         roof_step = {"bound": "hbm", "algo_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_total / K / 1e3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (ms_total / K / 1e3) / 1e9 / hbm_peak}
 
+    # ---- side measurements (N=1 only; parity-test configs of BASELINE.json, reported as extras, not the headline)
+    extras = None
+    if world == 1 and args.extras:
+        extras = {}
+        # (a) AR response tokens at 12k context: q = 1 steps, id fed back on the device side of the ABI
+        eng.kv_truncate(sid, KV_START)
+        one = torch.zeros(1, cfg.hidden_size, dtype=torch.bfloat16, device=dev)
+        tid = torch.tensor([1234], dtype=torch.int64, device=dev)
+        for _ in range(5):
+            eng.step([sid], [1], one, row_ids=tid)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        n_ar = 64
+        for _ in range(n_ar):
+            eng.step([sid], [1], one, row_ids=tid)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        extras["ar_decode"] = {"tokens_per_s": n_ar / (a0.elapsed_time(a1) / 1e3), "ms_per_token": a0.elapsed_time(a1) / n_ar,
+                               "kv_tokens": KV_START, "note": "greedy AR step (q=1) of one stream, device-timed, ids resident"}
+        # (b) configs[2]: 8 concurrent streams on one GPU (5-min clips -> kv ~6000), ViT batched over the streams,
+        #     one ragged decoder step of 8 x 11 tokens per tick
+        S8 = n_extra
+        sids = [sid] + [eng.stream_open() for _ in range(S8 - 1)]
+        for i, s_ in enumerate(sids):
+            eng.kv_fill_synthetic(s_, 6000, seed=100 + i)
+        packed8 = torch.zeros(11 * S8, cfg.hidden_size, dtype=torch.bfloat16, device=dev)
+        rid8 = prefix.repeat(S8)
+        def tick8(i):
+            fe = eng.vit_encode(frames_dev[i:i + S8])
+            packed8.view(S8, 11, -1)[:, 1:] = fe.view(S8, 10, -1)
+            eng.step(sids, [11] * S8, packed8, row_ids=rid8, want_logits=False)
+        for i in range(3):
+            tick8(i)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_t = min(10, (n_frames - S8) // 1)
+        b0.record(stream)
+        for i in range(n_t):
+            tick8(i)
+        b1.record(stream)
+        torch.cuda.synchronize()
+        extras["multistream8"] = {"frames_per_s": S8 * n_t / (b0.elapsed_time(b1) / 1e3), "ms_per_tick": b0.elapsed_time(b1) / n_t,
+                                  "streams": S8, "kv_tokens_start": 6000,
+                                  "note": "configs[2]: 8 concurrent streams/GPU, ViT batch 8 + one ragged 88-token decoder step per tick, device-timed"}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
-        return
+        return None
     fps = world * K / (ms_total / 1e3)
     e2e_fps = world * K / e2e_s
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -342,14 +413,31 @@ def run_engine_arm(args):
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(3 * S * S + 11 * 4 * 2 + 8), "d2h_bytes_per_step": 32,
                     "ms_per_step": 1e3 * e2e_s / K, "api": "LiveLlamaForCausalLM.visual_embed + Engine.step (vlo_vit_encode / vlo_step_ids) + read_decisions"},
             "roofline": roof, "roofline_attn": roof_attn, "roofline_step": roof_step, "kernel_classes": cls}
+    if extras:
+        line["extras"] = extras
     if world == 1 and not args.no_cpu_baseline:
         per_step, info = cpu_reference_times(2, 1)
         line["cpu_baseline"] = {"value": 1.0 / per_step, "unit": UNIT, "cores": info["threads"], "kind": "port",
                                 "sample": info["sample"], "host_cpus": os.cpu_count(),
                                 "vit_s_per_frame": info["vit_s_per_frame"], "decoder_s_per_step": info["decoder_s_per_step"]}
-    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    return line
+
+
+class _StdoutToStderr:
+    """Everything except the ONE JSON line goes to stderr (NCCL prints its version banner on stdout)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -359,11 +447,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the AR-decode / 8-stream side measurements")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_engine_arm(args)
+    with _StdoutToStderr() as guard:
+        line = run_reference_arm(args) if args.impl == "reference" else run_engine_arm(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -836,6 +836,58 @@ int vlo_step(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const int32
                       cuda_stream);
 }
 
+// ------------------------------------------------------------------------------ kernel-class micro loops
+// Back-to-back launches of ONE kernel class on the engine's real buffers and shapes (all layers, so the
+// working set is far larger than L2).  bench.py brackets the whole loop with one CUDA-event pair: the average
+// per launch then carries no per-launch event overhead and includes the PDL overlap the step really has.
+int vlo_bench_attn(vlo_engine* e, int stream_id, int n_tok, int iters, double* h_algo_bytes_per_launch, void* cuda_stream) {
+  VLO_CHECK(e != nullptr && e->finalized && e->has_decoder, "decoder weights not loaded");
+  if (check_stream(e, stream_id)) return -1;
+  const vlo_config& c = e->cfg;
+  const int kv_len = e->kv_len[stream_id];
+  VLO_CHECK(n_tok > 0 && n_tok <= c.max_step_tokens && kv_len >= n_tok, "bench_attn: need kv_len >= n_tok > 0");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  uint8_t* hs;
+  int slot;
+  if (stage_acquire(e, &hs, &slot)) return -1;
+  AttnSeq seq{0, n_tok, kv_len, static_cast<long long>(stream_id) * c.num_kv_heads * c.max_kv_tokens, c.max_kv_tokens};
+  AttnPlan plan{};
+  if (attn_plan(&plan, e->attn_ws, hs + e->meta_bytes, &seq, 1, n_tok, c.num_heads, c.num_kv_heads, c.head_dim, st)) return -1;
+  if (stage_release(e, slot, st)) return -1;
+  if (h_algo_bytes_per_launch) *h_algo_bytes_per_launch = plan.algo_bytes;
+  for (int it = 0; it < iters; ++it)
+    for (int l = 0; l < c.num_layers; ++l)
+      if (attn_run(plan, e->q, kv_layer_base(e, l, 0), kv_layer_base(e, l, 1), kv_rows_per_layer(c), e->attn_out, c.num_heads,
+                   c.num_kv_heads, c.head_dim, st))
+        return -1;
+  return 0;
+}
+
+int vlo_bench_gemm(vlo_engine* e, int n_tok, int iters, double* h_algo_bytes_per_iter, int* h_launches_per_iter,
+                   void* cuda_stream) {
+  VLO_CHECK(e != nullptr && e->finalized && e->has_decoder, "decoder weights not loaded");
+  const vlo_config& c = e->cfg;
+  VLO_CHECK(n_tok > 0 && n_tok <= c.max_step_tokens, "bench_gemm: n_tok out of range");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int H = c.hidden_size, I = c.intermediate_size, A = c.num_heads * c.head_dim;
+  double bytes = 0.0;
+  for (int it = 0; it < iters; ++it)
+    for (int l = 0; l < c.num_layers; ++l) {
+      const DecLayer& d = e->dec[l];
+      SkInfo sk{};
+      if (gemm_partial(e, d.qkv, e->qkv_width, e->xn, n_tok, H, &sk, st)) return -1;
+      if (gemm_partial(e, d.o, H, e->attn_out, n_tok, A, &sk, st)) return -1;
+      if (gemm_partial(e, d.gate_up, 2 * I, e->xn, n_tok, H, &sk, st)) return -1;
+      if (gemm_partial(e, d.down, H, e->act, n_tok, I, &sk, st)) return -1;
+      if (it == 0)
+        bytes += 2.0 * (static_cast<double>(e->qkv_width) * H + static_cast<double>(H) * A + 2.0 * I * H + static_cast<double>(H) * I) +
+                 2.0 * n_tok * (2.0 * H + A + I);
+    }
+  if (h_algo_bytes_per_iter) *h_algo_bytes_per_iter = bytes;
+  if (h_launches_per_iter) *h_launches_per_iter = 4 * c.num_layers;
+  return 0;
+}
+
 int vlo_last_step_hidden(vlo_engine* e, void* d_hidden, void* cuda_stream) {
   VLO_CHECK(e != nullptr && e->last_step_tokens > 0, "no decoder step has run");
   VLO_CUDA(cudaMemcpyAsync(d_hidden, e->xn, static_cast<size_t>(e->last_step_tokens) * e->cfg.hidden_size * sizeof(bf16),
