@@ -80,8 +80,6 @@ __device__ __forceinline__ float ex2_approx(float x) {  // one MUFU.EX2; inputs 
 
 struct AttnTcParams {
   AttnParams base;
-  int* counters;            // [n_items * n_kv_heads] arrival tickets, zero before launch, reset by the merging CTA
-  __nv_bfloat16* out;       // [n_tok, n_heads * 128] final attention output (written by the last CTA of each kv head)
   uint32_t v_lbo, v_sbo;  // V descriptor strides (bytes)
   long long* dbg;         // optional timeline buffer (VLO_ATTN_TRACE): [cta][role][64] clock64 stamps
 };
@@ -388,55 +386,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
       }
       if (r == 0) VLO_TC_STAMP(2, 2);
       tc_fence_before();
-      // ---- fused split-KV merge: the CTA that finishes LAST for this (item, kv head) combines all partials
-      __shared__ int s_last;
-      __threadfence();
-      asm volatile("bar.sync 2, 128;\n" ::: "memory");
-      if (r == 0) {
-        const int ticket = atomicAdd(&pp.counters[blockIdx.z * p.n_kv_heads + kvh], 1);
-        s_last = (ticket == it.n_splits - 1) ? 1 : 0;
-      }
-      asm volatile("bar.sync 2, 128;\n" ::: "memory");
-      if (s_last) {
-        __threadfence();
-        const int sw = q;  // softmax warp 0..3
-        const size_t slot_h = static_cast<size_t>(it.ws_slot0) + static_cast<size_t>(kvh) * it.n_splits * rows;
-        for (int row = sw; row < rows; row += 4) {
-          // weights of the splits for this row: lanes cover the splits (n_splits <= 148)
-          float mloc = -INFINITY;
-          for (int sidx = lane; sidx < it.n_splits; sidx += 32)
-            mloc = fmaxf(mloc, p.ws_ml[(slot_h + static_cast<size_t>(sidx) * rows + row) * 2]);
-          const float mx = warp_max(mloc);
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          float den = 0.f;
-          for (int s0 = 0; s0 < it.n_splits; s0 += 8) {
-            float4 o[8];
-            float w[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int sidx = s0 + k;
-              const bool ok = sidx < it.n_splits;
-              const size_t sl = slot_h + static_cast<size_t>(ok ? sidx : 0) * rows + row;
-              const float2 ml = ok ? *reinterpret_cast<const float2*>(p.ws_ml + sl * 2) : make_float2(-INFINITY, 0.f);
-              w[k] = (ml.x == -INFINITY) ? 0.f : exp2f((ml.x - mx) * c);
-              den += ml.y * w[k];
-              o[k] = ok ? *reinterpret_cast<const float4*>(p.ws_o + sl * kAttnHD + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              acc.x += o[k].x * w[k]; acc.y += o[k].y * w[k]; acc.z += o[k].z * w[k]; acc.w += o[k].w * w[k];
-            }
-          }
-          const float inv = 1.f / den;
-          const int tt = row / G, gg = row % G;
-          __nv_bfloat16* dst = pp.out + (static_cast<size_t>(it.q_tok0 + tt) * p.n_heads + kvh * G + gg) * kAttnHD + lane * 4;
-          uint2 wv;
-          *reinterpret_cast<__nv_bfloat162*>(&wv.x) = __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
-          *reinterpret_cast<__nv_bfloat162*>(&wv.y) = __floats2bfloat162_rn(acc.z * inv, acc.w * inv);
-          *reinterpret_cast<uint2*>(dst) = wv;
-        }
-        if (r == 0) pp.counters[blockIdx.z * p.n_kv_heads + kvh] = 0;  // ready for the next layer's launch
-      }
     }
   }
   __syncthreads();

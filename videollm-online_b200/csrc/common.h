@@ -137,7 +137,6 @@ struct AttnPlan {
   float* ws_ml;
   void* d_items;
   int* d_tok_item;
-  int* d_counters;    // per (item, kv head) arrival tickets for the fused merge (tcgen05 kernel)
   int n_items, max_splits, total_tokens;
   int version;        // 1 = mma.sync kernel, 2 = tcgen05 kernel
   double algo_bytes;  // algorithmic HBM bytes of one attn_run over this plan (K+V rows read, Q read, out written)
