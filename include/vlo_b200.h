@@ -141,10 +141,12 @@ int vlo_last_step_hidden(vlo_engine* e, void* d_hidden, void* cuda_stream);
 
 /* ------------------------------------------------------------------ measurement hooks (bench.py roofline)
  * Back-to-back launches of one kernel class on the engine's own buffers: the KV-append attention over every
- * layer's cache of `stream_id` (n_tok query rows at the end of the cache), and the four weight-streaming GEMMs
+ * layer's cache of the given streams (n_tok query rows at the end of each cache; skip_merge = 1 leaves out the
+ * split-KV merge kernel), and the four weight-streaming GEMMs
  * (qkv, o, gate_up, down) of every layer for n_tok token rows.  Asynchronous; the caller brackets the call with
  * CUDA events.  *h_algo_bytes = algorithmic HBM bytes per attention launch / per full pass over the layers. */
-int vlo_bench_attn(vlo_engine* e, int stream_id, int n_tok, int iters, double* h_algo_bytes_per_launch, void* cuda_stream);
+int vlo_bench_attn(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, int n_tok, int iters, int skip_merge,
+                   double* h_algo_bytes_per_launch, void* cuda_stream);
 int vlo_bench_gemm(vlo_engine* e, int n_tok, int iters, double* h_algo_bytes_per_iter, int* h_launches_per_iter,
                    void* cuda_stream);
 

@@ -194,6 +194,7 @@ static int attn_run_tc(const AttnPlan& plan, const void* d_q, const void* d_k, c
                       tk, tv, p));
   prof_end(stream);
   count_launch();
+  if (plan.skip_merge) return 0;
   return launch_merge(plan, d_out, n_heads, n_kv_heads, scale_log2, stream);
 }
 

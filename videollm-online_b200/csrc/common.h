@@ -139,6 +139,7 @@ struct AttnPlan {
   int* d_tok_item;
   int n_items, max_splits, total_tokens;
   int version;        // 1 = mma.sync kernel, 2 = tcgen05 kernel
+  int skip_merge;     // measurement only: launch the main kernel without the split-KV merge
   double algo_bytes;  // algorithmic HBM bytes of one attn_run over this plan (K+V rows read, Q read, out written)
 };
 // Build the work-item plan on the host and enqueue its upload.  h_stage (>= attn_stage_bytes())

@@ -840,20 +840,29 @@ int vlo_step(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const int32
 // Back-to-back launches of ONE kernel class on the engine's real buffers and shapes (all layers, so the
 // working set is far larger than L2).  bench.py brackets the whole loop with one CUDA-event pair: the average
 // per launch then carries no per-launch event overhead and includes the PDL overlap the step really has.
-int vlo_bench_attn(vlo_engine* e, int stream_id, int n_tok, int iters, double* h_algo_bytes_per_launch, void* cuda_stream) {
+int vlo_bench_attn(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, int n_tok, int iters, int skip_merge,
+                   double* h_algo_bytes_per_launch, void* cuda_stream) {
   VLO_CHECK(e != nullptr && e->finalized && e->has_decoder, "decoder weights not loaded");
-  if (check_stream(e, stream_id)) return -1;
   const vlo_config& c = e->cfg;
-  const int kv_len = e->kv_len[stream_id];
-  VLO_CHECK(n_tok > 0 && n_tok <= c.max_step_tokens && kv_len >= n_tok, "bench_attn: need kv_len >= n_tok > 0");
+  VLO_CHECK(n_seqs > 0 && n_seqs <= c.max_streams && n_tok > 0 && n_seqs * n_tok <= c.max_step_tokens, "bench_attn: sizes");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  std::vector<AttnSeq> seqs(n_seqs);
+  for (int i = 0; i < n_seqs; ++i) {
+    if (check_stream(e, h_stream_ids[i])) return -1;
+    const int kv_len = e->kv_len[h_stream_ids[i]];
+    VLO_CHECK(kv_len >= n_tok, "bench_attn: need kv_len >= n_tok");
+    seqs[i] = AttnSeq{i * n_tok, n_tok, kv_len, static_cast<long long>(h_stream_ids[i]) * c.num_kv_heads * c.max_kv_tokens,
+                      c.max_kv_tokens};
+  }
   uint8_t* hs;
   int slot;
   if (stage_acquire(e, &hs, &slot)) return -1;
-  AttnSeq seq{0, n_tok, kv_len, static_cast<long long>(stream_id) * c.num_kv_heads * c.max_kv_tokens, c.max_kv_tokens};
   AttnPlan plan{};
-  if (attn_plan(&plan, e->attn_ws, hs + e->meta_bytes, &seq, 1, n_tok, c.num_heads, c.num_kv_heads, c.head_dim, st)) return -1;
+  if (attn_plan(&plan, e->attn_ws, hs + e->meta_bytes, seqs.data(), n_seqs, n_seqs * n_tok, c.num_heads, c.num_kv_heads,
+                c.head_dim, st))
+    return -1;
   if (stage_release(e, slot, st)) return -1;
+  plan.skip_merge = skip_merge;
   if (h_algo_bytes_per_launch) *h_algo_bytes_per_launch = plan.algo_bytes;
   for (int it = 0; it < iters; ++it)
     for (int l = 0; l < c.num_layers; ++l)
