@@ -280,14 +280,24 @@ __global__ void __launch_bounds__(1024) decision_kernel(const __nv_bfloat16* log
       if (v > m2) m2 = v;
     }
   };
-  for (int vi = tid; vi < nvec; vi += blockDim.x) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(vi) * 8);
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  for (int v0 = tid; v0 < nvec; v0 += 4 * blockDim.x) {  // 4 independent 16-byte loads in flight per thread
+    uint4 raw[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
-      take(f.x, vi * 8 + 2 * k);
-      take(f.y, vi * 8 + 2 * k + 1);
+    for (int u = 0; u < 4; ++u) {
+      const int vi = v0 + u * blockDim.x;
+      raw[u] = vi < nvec ? *reinterpret_cast<const uint4*>(x + static_cast<size_t>(vi) * 8) : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int vi = v0 + u * blockDim.x;
+      if (vi >= nvec) break;
+      const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+        take(f.x, vi * 8 + 2 * k);
+        take(f.y, vi * 8 + 2 * k + 1);
+      }
     }
   }
   for (int idx = nvec * 8 + tid; idx < vocab; idx += blockDim.x) take(__bfloat162float(x[idx]), idx);
@@ -333,14 +343,24 @@ __global__ void __launch_bounds__(1024) decision_kernel(const __nv_bfloat16* log
     const float pz = (idx == interval_id) ? 0.f : pr;  // zero_() then argmax
     if (pz > pe) { pe = pz; ie = idx; }
   };
-  for (int vi = tid; vi < nvec; vi += blockDim.x) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(vi) * 8);
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  for (int v0 = tid; v0 < nvec; v0 += 4 * blockDim.x) {
+    uint4 raw[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
-      prob(f.x, vi * 8 + 2 * k);
-      prob(f.y, vi * 8 + 2 * k + 1);
+    for (int u = 0; u < 4; ++u) {
+      const int vi = v0 + u * blockDim.x;
+      raw[u] = vi < nvec ? *reinterpret_cast<const uint4*>(x + static_cast<size_t>(vi) * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int vi = v0 + u * blockDim.x;
+      if (vi >= nvec) break;
+      const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+        prob(f.x, vi * 8 + 2 * k);
+        prob(f.y, vi * 8 + 2 * k + 1);
+      }
     }
   }
   for (int idx = nvec * 8 + tid; idx < vocab; idx += blockDim.x) prob(__bfloat162float(x[idx]), idx);

@@ -434,7 +434,15 @@ __global__ void __launch_bounds__(128) probe_attn_kernel(const __half* kv, const
   const int d = tid & 63, hf = tid >> 6;
   const __half* vb = kb + C + d;
   float acc = 0.f;
-  for (int n = hf; n < N; n += 2) acc += sc[n] * __half2float(vb[static_cast<size_t>(n) * 2 * C]);
+  int n = hf;
+  for (; n + 14 < N; n += 16) {  // 8 independent loads in flight
+    float x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = __half2float(vb[static_cast<size_t>(n + 2 * u) * 2 * C]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += sc[n + 2 * u] * x[u];
+  }
+  for (; n < N; n += 2) acc += sc[n] * __half2float(vb[static_cast<size_t>(n) * 2 * C]);
   part[hf][d] = acc;
   __syncthreads();
   if (tid < kVitHD) out[static_cast<size_t>(b) * C + head * kVitHD + tid] = __float2half_rn((part[0][tid] + part[1][tid]) / sum);

@@ -58,6 +58,12 @@ class LiveInfer:
         # (random weights never emit the "]\\n" / EOS protocol ids); None in production.
         self.decision_hook = None
         self._n_calls = 0
+        # encode-ahead: with a loaded clip the ViT + connector of the NEXT frame run on a side CUDA stream while the
+        # decoder works on the current one (same per-frame arithmetic; a live stream delivers the next frame
+        # during the current step anyway).  Set prefetch_next = False for strictly sequential behaviour.
+        self.prefetch_next = True
+        self._side = torch.cuda.Stream(self.device)
+        self._prefetched = None   # (frame_idx, embeds tensor, event)
         self.reset()
 
     # ------------------------------------------------------------------ session control
@@ -70,6 +76,7 @@ class LiveInfer:
         self.last_ids = torch.tensor([[]], dtype=torch.long)
         self._kv.engine.stream_reset(self._kv.stream_id)
         self.past_key_values = None
+        self._prefetched = None
 
     def load_video(self, video_path_or_tensor):
         """Reference: read_video(...)[0].to('cuda') (demo/inference.py:111-115).  Accepts a uint8
@@ -94,8 +101,26 @@ class LiveInfer:
         frame_idx = int(video_time * self.frame_fps)
         if frame_idx > self.last_frame_idx:
             ranger = range(self.last_frame_idx + 1, frame_idx + 1)
-            embeds = self.model.visual_embed(self.video_tensor[ranger.start:ranger.stop]).split(self.frame_num_tokens)
+            start, embeds = ranger.start, []
+            main = torch.cuda.current_stream(self.device)
+            if self._prefetched is not None and self._prefetched[0] == start:
+                _, pe, ev = self._prefetched
+                main.wait_event(ev)
+                pe.record_stream(main)
+                embeds.append(pe)
+                start += 1
+            self._prefetched = None
+            if start < ranger.stop:
+                embeds.extend(self.model.visual_embed(self.video_tensor[start:ranger.stop]).split(self.frame_num_tokens))
             self.frame_embeds_queue.extend([(r / self.frame_fps, e) for r, e in zip(ranger, embeds)])
+            nxt = frame_idx + 1
+            if self.prefetch_next and self.video_tensor is not None and nxt < self.video_tensor.size(0):
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    pe = self.model.visual_embed(self.video_tensor[nxt:nxt + 1])
+                    ev = torch.cuda.Event()
+                    ev.record(self._side)
+                self._prefetched = (nxt, pe, ev)
         self.last_frame_idx = frame_idx
         self.video_time = video_time
 
