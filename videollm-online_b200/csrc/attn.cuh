@@ -48,8 +48,8 @@ struct AttnParams {
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_kvappend_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                      const AttnParams p) {
-  pdl_wait();   // the work items (uploaded this step) and the freshly appended K/V rows come from predecessors
   pdl_trigger();
+  pdl_wait();   // the freshly appended K/V rows and Q come from predecessors
   const AttnItem it = p.items[blockIdx.z];
   const int split = blockIdx.x;
   if (split >= it.n_splits) return;
@@ -318,8 +318,8 @@ __global__ void __launch_bounds__(128) attn_merge_kernel(const AttnMergeParams p
   __shared__ float s_m[160], s_w[160];
   __shared__ float s_den;
   const int head = blockIdx.x, tok = blockIdx.y, d = threadIdx.x;
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   const AttnItem it = p.items[p.tok_item[tok]];
   const int G = p.n_heads / p.n_kv_heads;
   const int kvh = head / G, g = head % G;

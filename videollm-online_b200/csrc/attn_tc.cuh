@@ -144,10 +144,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // after the TMEM allocation (see gemm_ws.cuh); successors may start their prologues
 
-  // Work item and split geometry.  The item table was uploaded at the start of the step, i.e. by an operation
-  // older than our immediate predecessor kernel, so it may be read before pdl_wait() (every kernel of the
-  // step triggers only after its own wait; see ptx.cuh).
+  // Work item and split geometry.  The item table was uploaded by a memcpy at the start of the step; a memcpy is a
+  // full stream-order dependency for the first kernel of the step, so it is complete before ANY kernel of the
+  // step runs and may be read before pdl_wait().
   const AttnItem it = p.items[blockIdx.z];
   const int split = blockIdx.x;
   const int kvh = blockIdx.y;
@@ -160,8 +161,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   const uint32_t tS = tmem_base, tO = tmem_base + 256;
   const int row_base = it.kv_row0 + kvh * it.kv_head_stride;
 
-  // K/V rows of EARLIER steps do not depend on the predecessor either (only the rows appended in this step
-  // do): prefetch the first blocks that end safely below this step's new tokens before waiting.
+  // K/V rows of EARLIER steps do not depend on any kernel of this step (only the rows appended in this step
+  // do; the previous step finished before this step's first memcpy): prefetch the first blocks that end safely
+  // below this step's new tokens before waiting.
   int pre = 0;
   if (warp == 0 && lane == 0) {
     const int safe_end = it.q_pos0 - 128;  // a step appends at most 128 tokens per stream
@@ -179,7 +181,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   }
   if (threadIdx.x == 0) VLO_TC_STAMP(0, 1);
   pdl_wait();
-  pdl_trigger();
   if (threadIdx.x == 0) VLO_TC_STAMP(0, 2);
 
   if (nblk > 0) {

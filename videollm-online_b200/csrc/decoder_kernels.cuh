@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(1024) resid_rmsnorm_kernel(const ResidNormPara
   __shared__ float red[32];
   const int t = blockIdx.x;
   __nv_bfloat16* h = p.h + static_cast<size_t>(t) * p.H;
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   float ss = 0.f;
   for (int i = threadIdx.x * 4; i < p.H; i += blockDim.x * 4) {
     const uint2 hraw = *reinterpret_cast<const uint2*>(h + i);
@@ -130,8 +130,8 @@ struct QkvRopeParams {
 
 __global__ void __launch_bounds__(64) qkv_rope_append_kernel(const QkvRopeParams p) {
   const int t = blockIdx.x, hh = blockIdx.y, d = threadIdx.x;
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   const int width = (p.n_heads + 2 * p.n_kv_heads) * 128;
   const float* pp = p.part + static_cast<size_t>(t) * width + hh * 128 + d;
   float x1 = 0.f, x2 = 0.f;
@@ -175,8 +175,8 @@ struct SwigluParams {
   int T, I;
 };
 __global__ void __launch_bounds__(256) swiglu_kernel(const SwigluParams p) {
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   const long long n4 = static_cast<long long>(p.T) * p.I / 4;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n4;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -262,8 +262,8 @@ __global__ void __launch_bounds__(1024) decision_kernel(const __nv_bfloat16* log
   __shared__ int s_i1[32], s_ia[32], s_ie[32];
   __shared__ float s_gmax, s_gmax2, s_sum;
   __shared__ int s_gidx;
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   const __nv_bfloat16* x = logits + static_cast<size_t>(blockIdx.x) * vocab;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int nvec = vocab / 8;  // rows are 16-byte aligned (vocab % 8 == 0 checked by the engine); tail handled below

@@ -136,8 +136,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // after the TMEM allocation
   pdl_wait();
-  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {

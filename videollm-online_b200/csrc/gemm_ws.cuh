@@ -34,7 +34,8 @@ struct GemmWsArgs {
 
 template <int BN>
 struct GemmWsCfg {
-  static constexpr int kStages = BN <= 64 ? 8 : (BN <= 96 ? 7 : (BN <= 128 ? 6 : 5));
+  // <= ~110 KB per CTA for BN <= 64 so that two CTAs (this GEMM's tail + the next GEMM's prefetching head) share an SM
+  static constexpr int kStages = BN <= 32 ? 6 : (BN <= 64 ? 4 : (BN <= 96 ? 7 : (BN <= 128 ? 6 : 5)));
   static constexpr int kBytesA = kGemmBM * kGemmBK * 2;
   static constexpr int kBytesB = BN * kGemmBK * 2;
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
@@ -42,7 +43,7 @@ struct GemmWsCfg {
 };
 
 template <int FMT, int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, BN <= 64 ? 2 : 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                const GemmWsArgs p) {
   using Cfg = GemmWsCfg<BN>;
@@ -88,8 +89,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // The weight operand never depends on the predecessor kernel: the producer starts streaming the first
-  // S weight k-blocks right away, i.e. while the previous (small fix-up) kernel is still running.
+  // Our TMEM is allocated: successors may be scheduled now (never before the allocation: a successor that grabbed
+  // this SM's TMEM first while we still had to allocate would dead-lock us).  Early triggering lets the next kernels of
+  // the step become resident and prefetch while this one streams.
+  pdl_trigger();
+  // The weight operand never depends on any earlier kernel: the producer starts streaming the first S weight
+  // k-blocks right away, i.e. while the predecessors are still running.
   int pre = 0;
   if (warp == 0 && lane == 0) {
     for (long long u = u0; u < u1 && pre < S; ++u, ++pre) {
@@ -100,9 +105,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       tma_load_2d(smem_a + pre * Cfg::kBytesA, &tm_w, &full_bar[pre], kblk * kGemmBK, wt * kGemmBM, p.hint_w);
     }
   }
-  // everything above overlapped the previous kernel's tail; its results (the activations) are needed from here on
+  // everything above overlapped the predecessors; their results (the activations) are needed from here on
   pdl_wait();
-  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {

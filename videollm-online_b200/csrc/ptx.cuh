@@ -163,7 +163,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int fmt, int m, int n) {
 // predecessor in the stream is still running; it must execute pdl_wait() before touching anything the
 // predecessor produces (the wait returns once the predecessor grid has completed and flushed).
 // pdl_trigger() lets the successor start being scheduled; everything before pdl_wait() in the
-// successor (barrier init, TMEM allocation, descriptor prefetch) then overlaps this grid's tail.
+// successor (barrier init, TMEM allocation, descriptor prefetch, weight / old-KV prefetch) then overlaps
+// this grid.  Rules used throughout the step:
+//   * trigger EARLY (kernel entry, or right after the TMEM allocation for kernels that allocate TMEM — a
+//     successor must never be able to take an SM's TMEM before a CTA of this grid that still has to allocate);
+//   * before pdl_wait() a kernel only reads data that no kernel of the current step writes (weights, the
+//     per-step tables uploaded by memcpy before the step's first kernel, K/V rows of earlier steps) and
+//     writes nothing to global memory.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 

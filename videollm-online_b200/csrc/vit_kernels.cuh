@@ -16,8 +16,8 @@ namespace vlo {
 // (models/vision_live.py:12; column order = conv weight [C,3,ps,ps] flattened,
 //  HF:...siglip.py:175-179).  One thread per 8 horizontally adjacent pixels.
 __global__ void __launch_bounds__(256) patchify_kernel(const uint8_t* frames, __half* out, int B, int S, int ps) {
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   const int g = S / ps, P = g * g, K = 3 * ps * ps;
   const long long total = static_cast<long long>(B) * P * K / 8;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(256) patchify_kernel(const uint8_t* frames, __
 template <typename InT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const InT* in, const float* w, const float* b, __half* out16,
                                                         float* out32, int C, float eps) {
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   extern __shared__ float row[];
   __shared__ float red[32];
   const size_t r = blockIdx.x;
@@ -105,8 +105,8 @@ struct VitFixLnParams {
   float eps;
 };
 __global__ void __launch_bounds__(256) vit_fix_ln_kernel(const VitFixLnParams p) {
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   // 4 contiguous channels per thread per sweep; the (<= 8) plane loads of a sweep are independent.
   extern __shared__ float row[];
   __shared__ float red[32];
@@ -226,8 +226,8 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half* out, int N, 
     fence_mbar_init();
   }
   __syncthreads();
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -368,8 +368,8 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half* out, int N, 
 // written into the token buffer after the optional CLS slot.  in: fp32 [B, g*g, C].
 __global__ void __launch_bounds__(256) pool_kernel(const float* in, float* tokens, int B, int g, int C, int ph, int pw,
                                                    int n_tok, int tok_off) {
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   const long long total = static_cast<long long>(B) * ph * pw * C;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* in, float* token
 // grid = (heads, B), block = 128; dynamic smem = N floats.
 __global__ void __launch_bounds__(128) probe_attn_kernel(const __half* kv, const float* q, __half* out, int N, int C,
                                                          float scale) {
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   extern __shared__ float sc[];
   __shared__ float red[4];
   __shared__ float part[2][kVitHD];
@@ -453,8 +453,8 @@ __global__ void __launch_bounds__(128) probe_attn_kernel(const __half* kv, const
 // models/modeling_live.py:25).
 __global__ void __launch_bounds__(256) cls_residual_kernel(const __half* resid, const __half* mlp, float* tokens, int B,
                                                            int C, int n_tok) {
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   const int total = B * C;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int b = idx / C, c = idx % C;
@@ -463,8 +463,8 @@ __global__ void __launch_bounds__(256) cls_residual_kernel(const __half* resid, 
   }
 }
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* in, __nv_bfloat16* out, long long n) {
-  pdl_wait();
   pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
