@@ -6,6 +6,8 @@
 
 #include <cudaTypedefs.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -212,6 +214,13 @@ int launch_ws(const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsArgs& a,
   static bool attr_set = false;
   if (!attr_set) {
     VLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmWsCfg<BN>::kSmemBytes));
+    if (BN <= 64)  // two CTAs per SM (tail of one GEMM + prefetching head of the next): ask for the full carve-out
+      VLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (getenv("VLO_DEBUG")) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kGemmThreads, GemmWsCfg<BN>::kSmemBytes);
+      fprintf(stderr, "vlo: gemm_ws<%d,%d> smem %d B -> %d CTA/SM\n", FMT, BN, GemmWsCfg<BN>::kSmemBytes, nb);
+    }
     attr_set = true;
   }
   if (prof_on()) {
