@@ -214,8 +214,6 @@ int launch_ws(const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsArgs& a,
   static bool attr_set = false;
   if (!attr_set) {
     VLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmWsCfg<BN>::kSmemBytes));
-    if (BN <= 64)  // two CTAs per SM (tail of one GEMM + prefetching head of the next): ask for the full carve-out
-      VLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (getenv("VLO_DEBUG")) {
       int nb = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kGemmThreads, GemmWsCfg<BN>::kSmemBytes);
