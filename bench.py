@@ -34,6 +34,18 @@ WORKLOAD = ("configs[1]: 1 stream/GPU, SigLIP-L/16-384 + Llama-3-8B, frame step 
 
 
 # ----------------------------------------------------------------------------- helpers
+def _ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full summaries
+    (profiles/ncu_traffic.json, written by tools/profile_summary.py from the .ncu-rep files), or None."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return None
+    try:
+        return json.loads(p.read_text()).get(kernel_key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -374,14 +386,14 @@ def run_engine_arm(args):
         gs, at = cls.get("gemm_weight_stream"), cls.get("attn_kvappend")
         roof = {"bound": "hbm", "kernel": "gemm_ws_kernel<bf16> (persistent stream-K weight streaming: 14.0 GB of the 16.6 GB/step)",
                 "achieved": micro_gemm["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": micro_gemm["achieved_gbs"] / hbm_peak,
-                "peak_source": which, "traffic": None,
+                "peak_source": which, "traffic": _ncu_traffic("gemm_ws_decoder"),
                 "avg_us_per_launch": micro_gemm["us_per_launch"], "algo_bytes_per_launch": micro_gemm["algo_bytes_per_launch"],
                 "method": "CUDA events around 4 back-to-back passes of the 128 decoder GEMM launches (q|k|v, o, gate|up, down of all 32 layers) on the engine's buffers, T=11",
                 "in_step_event_bracketed": {"achieved": gs["achieved_gbs"], "avg_us_per_launch": gs["avg_us_per_launch"],
                                             "note": "per-launch event pairs inside the step (PDL off): includes ~3-5 us bracket overhead per launch"}}
         roof_attn = {"bound": "hbm", "kernel": "attn_tc_kernel + attn_merge_kernel (KV-append attention, tcgen05; one launch pair per layer)",
                      "achieved": micro_attn["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": micro_attn["achieved_gbs"] / hbm_peak,
-                     "peak_source": which, "traffic": None, "avg_us_per_launch": micro_attn["us_per_launch_incl_merge"],
+                     "peak_source": which, "traffic": _ncu_traffic("attn_tc"), "avg_us_per_launch": micro_attn["us_per_launch_incl_merge"],
                      "algo_bytes_per_launch": micro_attn["algo_bytes_per_launch"],
                      "method": "CUDA events around 4x32 back-to-back launch pairs over the 32 layers' caches (1.6 GB, > L2), q=11, kv=12011; merge kernel time included",
                      "main_kernel_only": {"achieved": micro_attn["achieved_gbs_main_only"], "frac": micro_attn["achieved_gbs_main_only"] / hbm_peak,

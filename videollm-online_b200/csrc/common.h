@@ -114,6 +114,7 @@ struct GemmWsCall {
   SkInfo sk;          // from gemm_ws_plan
   int bn;             // token-tile width (0 = smallest of 16/32/64/128 covering rows_x); 96 / 192 for the ViT
   int weights_hot;    // 1: weights are re-read by several token tiles (keep them in L2)
+  int small_smem;     // 1: shallow 3-stage ring (~75 KB) so the CTA can share an SM with a decoder weight-streaming CTA
 };
 // decomposition for (rows_w, k): n_ctas <= 0 -> one CTA per SM; max_planes = fp32 planes the partials need
 int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_planes, int x_tiles = 1);

@@ -1,6 +1,7 @@
 // vlo_engine: weights registry, KV-cache ownership, workspaces and the orchestration of the
 // per-frame hot path (vlo_vit_encode, vlo_step) on one GPU.  See include/vlo_b200.h for the ABI
 // and DESIGN.md for the memory layout.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -536,7 +537,17 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
   // MMA-N): QKV and fc1 run whole tiles with the fused bias / GELU fp16 epilogue; out_proj and fc2 (few
   // output tiles) run stream-K over all SMs and their partial planes are folded into the fp32 residual
   // stream together with the NEXT LayerNorm by vit_fix_ln_kernel.
+  // Small batches (the single-stream case) run the trunk GEMMs with 64-token tiles and a shallow ring (~75 KB of
+  // shared memory): such a CTA fits on an SM NEXT TO a decoder weight-streaming CTA (145 KB), so the tensor-bound
+  // ViT of frame i+1 and the HBM-bound decoder step of frame i really execute concurrently (two CUDA streams).
+  static int coreside = -1;
+  if (coreside < 0) {
+    const char* ev = getenv("VLO_VIT_CORESIDE");
+    coreside = (ev != nullptr && ev[0] == '0') ? 0 : 1;
+  }
+  const bool small = coreside && B <= 2;
   auto pick_bn = [&](int n_out, int mode) {
+    if (small) return 64;
     const int cands[4] = {64, 96, 128, 192};
     int best = 64;
     double best_eff = -1.0;
@@ -567,6 +578,7 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     g.act = act;
     g.bn = pick_bn(n_out, 1);
     g.weights_hot = 1;
+    g.small_smem = small ? 1 : 0;
     gemm_ws_plan(n_out, k, 1, 0, &g.sk, nullptr, (rows + g.bn - 1) / g.bn);
     return gemm_ws_launch(g, st);
   };
@@ -585,6 +597,7 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     g.plane_stride = static_cast<long long>(rows) * C;
     g.bn = pick_bn(C, 0);
     g.weights_hot = 1;
+    g.small_smem = small ? 1 : 0;
     int planes = 1;
     out->bn = g.bn;
     out->xt = (rows + g.bn - 1) / g.bn;

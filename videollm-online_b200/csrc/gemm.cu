@@ -208,16 +208,16 @@ int num_sms() {
   return n;
 }
 
-template <int FMT, int BN>
+template <int FMT, int BN, int STAGES = ws_default_stages(BN)>
 int launch_ws(const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsArgs& a, cudaStream_t stream) {
-  auto kern = gemm_ws_kernel<FMT, BN>;
+  auto kern = gemm_ws_kernel<FMT, BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    VLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmWsCfg<BN>::kSmemBytes));
+    VLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmWsCfg<BN, STAGES>::kSmemBytes));
     if (getenv("VLO_DEBUG")) {
       int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kGemmThreads, GemmWsCfg<BN>::kSmemBytes);
-      fprintf(stderr, "vlo: gemm_ws<%d,%d> smem %d B -> %d CTA/SM\n", FMT, BN, GemmWsCfg<BN>::kSmemBytes, nb);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kGemmThreads, GemmWsCfg<BN, STAGES>::kSmemBytes);
+      fprintf(stderr, "vlo: gemm_ws<%d,%d> smem %d B -> %d CTA/SM\n", FMT, BN, GemmWsCfg<BN, STAGES>::kSmemBytes, nb);
     }
     attr_set = true;
   }
@@ -226,7 +226,7 @@ int launch_ws(const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsArgs& a,
     prof_begin(FMT == FMT_BF16 ? PROF_GEMM_STREAM : PROF_GEMM_VIT, stream,
                2.0 * a.k * (static_cast<double>(a.rows_w) + a.rows_x) + out_b);
   }
-  VLO_CUDA(launch_pdl(kern, dim3(a.sk.G), dim3(kGemmThreads), GemmWsCfg<BN>::kSmemBytes, stream, tw, tx, a));
+  VLO_CUDA(launch_pdl(kern, dim3(a.sk.G), dim3(kGemmThreads), GemmWsCfg<BN, STAGES>::kSmemBytes, stream, tw, tx, a));
   prof_end(stream);
   count_launch();
   return 0;
@@ -275,6 +275,27 @@ int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream) {
   if (get_tmap(c.x, c.rows_x, c.k, bn, c.fmt, &tx) != 0) return -1;
 #define VLO_WS_CASE(F, N) \
   if (c.fmt == F && bn == N) return launch_ws<F, N>(tw, tx, a, stream);
+  if (c.fmt == FMT_BF16 && bn == 16) {  // ring depth of the single-stream decoder GEMM: A/B switch (VLO_WS_STAGES=6|8|11)
+    static int st = 0;
+    if (st == 0) {
+      const char* e = getenv("VLO_WS_STAGES");
+      st = e ? atoi(e) : 6;
+    }
+    // 6 x 18 KB (measured best in the two-stream pipelined step: leaves room for a co-resident ViT CTA)
+    if (st == 4) return launch_ws<FMT_BF16, 16, 4>(tw, tx, a, stream);
+    if (st == 5) return launch_ws<FMT_BF16, 16, 5>(tw, tx, a, stream);
+    if (st == 6) return launch_ws<FMT_BF16, 16, 6>(tw, tx, a, stream);
+    if (st == 11) return launch_ws<FMT_BF16, 16, 11>(tw, tx, a, stream);
+  }
+  if (c.fmt == FMT_F16 && bn == 64 && c.small_smem) {
+    static int vst = 0;
+    if (vst == 0) {
+      const char* e = getenv("VLO_VIT_STAGES");
+      vst = e ? atoi(e) : 3;
+    }
+    if (vst == 4) return launch_ws<FMT_F16, 64, 4>(tw, tx, a, stream);
+    return launch_ws<FMT_F16, 64, 3>(tw, tx, a, stream);
+  }
   VLO_WS_CASE(FMT_BF16, 16)
   VLO_WS_CASE(FMT_BF16, 32)
   VLO_WS_CASE(FMT_BF16, 64)

@@ -32,21 +32,22 @@ struct GemmWsArgs {
   unsigned long long hint_w;  // L2 policy for the weight stream (evict-first when read once per launch)
 };
 
-template <int BN>
+constexpr int ws_default_stages(int bn) { return bn <= 64 ? 8 : (bn <= 96 ? 7 : (bn <= 128 ? 6 : 5)); }
+
+template <int BN, int STAGES = ws_default_stages(BN)>
 struct GemmWsCfg {
-  // deep ring: measured on the lm_head stream, 8 x 18 KB stages in flight per SM give 5.9 TB/s, 6 stages only 5.4 TB/s
-  static constexpr int kStages = BN <= 64 ? 8 : (BN <= 96 ? 7 : (BN <= 128 ? 6 : 5));
+  static constexpr int kStages = STAGES;
   static constexpr int kBytesA = kGemmBM * kGemmBK * 2;
   static constexpr int kBytesB = BN * kGemmBK * 2;
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * (kBytesA + kBytesB) + 1024 + 256;
 };
 
-template <int FMT, int BN>
+template <int FMT, int BN, int STAGES = ws_default_stages(BN)>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                const GemmWsArgs p) {
-  using Cfg = GemmWsCfg<BN>;
+  using Cfg = GemmWsCfg<BN, STAGES>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
