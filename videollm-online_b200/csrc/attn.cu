@@ -52,8 +52,7 @@ size_t attn_ws_bytes(int total_tokens, int n_seqs, int n_heads, int n_kv_heads) 
   const int G = n_heads / n_kv_heads;
   const size_t slots = cap_slots_for(total_tokens, n_seqs, n_heads, n_kv_heads);
   return align_up(slots * kAttnHD * 4) + align_up(slots * 2 * 4) +
-         align_up(sizeof(AttnItem) * max_chunks(total_tokens, n_seqs, G)) + align_up(sizeof(int) * total_tokens) +
-         align_up(sizeof(int) * 2 * static_cast<size_t>(max_chunks(total_tokens, n_seqs, G)) * n_kv_heads);
+         align_up(sizeof(AttnItem) * max_chunks(total_tokens, n_seqs, G)) + align_up(sizeof(int) * total_tokens);
 }
 
 int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, int n_seqs, int total_tokens,
@@ -116,13 +115,6 @@ int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, in
   plan->d_items = w;
   w += align_up(sizeof(AttnItem) * max_chunks(total_tokens, n_seqs, G));
   plan->d_tok_item = reinterpret_cast<int*>(w);
-  w += align_up(sizeof(int) * total_tokens);
-  plan->d_counters = reinterpret_cast<int*>(w);
-  // fused in-kernel merge needs the whole grid co-resident (spin-wait between the CTAs of a kv head)
-  plan->fused_merge = (version == 2 && static_cast<long long>(max_splits) * n_kv_heads * n_items <= kNumSMs) ? 1 : 0;
-  if (const char* ev = getenv("VLO_ATTN_FUSED_MERGE")) plan->fused_merge = plan->fused_merge && ev[0] != '0';
-  if (plan->fused_merge)
-    VLO_CUDA(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * 2 * static_cast<size_t>(n_items) * n_kv_heads, stream));
   plan->n_items = n_items;
   plan->max_splits = max_splits;
   plan->total_tokens = total_tokens;
@@ -195,8 +187,6 @@ static int attn_run_tc(const AttnPlan& plan, const void* d_q, const void* d_k, c
     p.dbg = dbg;
     g_attn_trace = dbg;
   }
-  p.counters = plan.fused_merge ? plan.d_counters : nullptr;
-  p.out = static_cast<__nv_bfloat16*>(d_out);
   p.v_lbo = swap_ls ? 1024u : static_cast<uint32_t>(kTcSub);
   p.v_sbo = swap_ls ? static_cast<uint32_t>(kTcSub) : 1024u;
   prof_begin(PROF_ATTN, stream, plan.algo_bytes);
@@ -204,7 +194,7 @@ static int attn_run_tc(const AttnPlan& plan, const void* d_q, const void* d_k, c
                       tk, tv, p));
   prof_end(stream);
   count_launch();
-  if (plan.skip_merge || plan.fused_merge) return 0;
+  if (plan.skip_merge) return 0;
   return launch_merge(plan, d_out, n_heads, n_kv_heads, scale_log2, stream);
 }
 

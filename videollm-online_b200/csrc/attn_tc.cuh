@@ -80,8 +80,6 @@ __device__ __forceinline__ float ex2_approx(float x) {  // one MUFU.EX2; inputs 
 
 struct AttnTcParams {
   AttnParams base;
-  int* counters;            // fused merge: [n_items * n_kv_heads][2] (arrived, merged) tickets; null = separate merge kernel
-  __nv_bfloat16* out;       // fused merge: final attention output [n_tok, n_heads * 128]
   uint32_t v_lbo, v_sbo;  // V descriptor strides (bytes)
   long long* dbg;         // optional timeline buffer (VLO_ATTN_TRACE): [cta][role][64] clock64 stamps
 };
@@ -389,65 +387,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
       }
       if (r == 0) VLO_TC_STAMP(2, 2);
       tc_fence_before();
-      if (pp.counters != nullptr) {
-        // ---- fused, distributed split-KV merge (the whole grid is co-resident: one CTA per SM, grid <= #SMs).
-        // Every CTA of this (item, kv head) announces its partials, waits until all n_splits are there and then
-        // merges the rows  split, split + n_splits, ...  (one row per softmax warp): the merge work is spread
-        // over the CTAs that produced the partials and no second kernel launch is needed.
-        int* cnt = pp.counters + (static_cast<size_t>(blockIdx.z) * p.n_kv_heads + kvh) * 2;
-        __threadfence();
-        asm volatile("bar.sync 2, 128;\n" ::: "memory");
-        if (r == 0) {
-          atomicAdd(cnt, 1);
-          unsigned ns = 8;
-          while (*reinterpret_cast<volatile int*>(cnt) < it.n_splits) {
-            __nanosleep(ns);
-            if (ns < 256) ns *= 2;
-          }
-        }
-        asm volatile("bar.sync 2, 128;\n" ::: "memory");
-        __threadfence();
-        const size_t slot_h = static_cast<size_t>(it.ws_slot0) + static_cast<size_t>(kvh) * it.n_splits * rows;
-        for (int row = split + q * it.n_splits; row < rows; row += 4 * it.n_splits) {
-          float mloc = -INFINITY;
-          for (int sidx = lane; sidx < it.n_splits; sidx += 32)
-            mloc = fmaxf(mloc, __ldcg(p.ws_ml + (slot_h + static_cast<size_t>(sidx) * rows + row) * 2));
-          const float mx = warp_max(mloc);
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          float den = 0.f;
-          for (int s0 = 0; s0 < it.n_splits; s0 += 8) {
-            float4 o[8];
-            float w[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int sidx = s0 + k;
-              const bool ok = sidx < it.n_splits;
-              const size_t sl = slot_h + static_cast<size_t>(ok ? sidx : 0) * rows + row;
-              const float2 ml = ok ? __ldcg(reinterpret_cast<const float2*>(p.ws_ml + sl * 2)) : make_float2(-INFINITY, 0.f);
-              w[k] = (ml.x == -INFINITY) ? 0.f : exp2f((ml.x - mx) * c);
-              den += ml.y * w[k];
-              o[k] = ok ? __ldcg(reinterpret_cast<const float4*>(p.ws_o + sl * kAttnHD + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              acc.x += o[k].x * w[k]; acc.y += o[k].y * w[k]; acc.z += o[k].z * w[k]; acc.w += o[k].w * w[k];
-            }
-          }
-          const float inv = 1.f / den;
-          const int tt = row / G, gg = row % G;
-          __nv_bfloat16* dst = pp.out + (static_cast<size_t>(it.q_tok0 + tt) * p.n_heads + kvh * G + gg) * kAttnHD + lane * 4;
-          uint2 wv;
-          *reinterpret_cast<__nv_bfloat162*>(&wv.x) = __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
-          *reinterpret_cast<__nv_bfloat162*>(&wv.y) = __floats2bfloat162_rn(acc.z * inv, acc.w * inv);
-          *reinterpret_cast<uint2*>(dst) = wv;
-        }
-        // the last CTA to finish its share re-arms the tickets for the next layer's launch
-        asm volatile("bar.sync 2, 128;\n" ::: "memory");
-        if (r == 0 && atomicAdd(cnt + 1, 1) == it.n_splits - 1) {
-          cnt[0] = 0;
-          cnt[1] = 0;
-        }
-      }
     }
   }
   __syncthreads();

@@ -138,8 +138,6 @@ struct AttnPlan {
   float* ws_ml;
   void* d_items;
   int* d_tok_item;
-  int* d_counters;    // (arrived, merged) tickets per (item, kv head) for the fused in-kernel merge
-  int fused_merge;    // 1: the tcgen05 kernel merges its own partials (whole grid co-resident), no merge launch
   int n_items, max_splits, total_tokens;
   int version;        // 1 = mma.sync kernel, 2 = tcgen05 kernel
   int skip_merge;     // measurement only: launch the main kernel without the split-KV merge
