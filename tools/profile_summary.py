@@ -56,8 +56,33 @@ def metrics(src, dst):
     print(open(dst).read()[:1500])
 
 
+def traffic(dst, *pairs):
+    """pairs: key=report.ncu-rep[:name-substring] -> profiles/ncu_traffic.json with mean dram bytes per launch"""
+    import json
+    out = {}
+    for pr in pairs:
+        key, rest = pr.split("=", 1)
+        rep, _, sub = rest.partition(":")
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        r = list(csv.reader(raw.splitlines()))
+        hdr, units = r[0], r[1]
+        ir, iw, it, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum"), hdr.index("Kernel Name")
+        def to_b(v, u):
+            v = float(v)
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        rows = [x for x in r[2:] if sub in x[ik]]
+        tot = [to_b(x[ir], units[ir]) + to_b(x[iw], units[iw]) for x in rows]
+        dur = [float(x[it]) for x in rows]
+        out[key] = {"dram_bytes_per_launch": sum(tot) / max(1, len(tot)), "launches": len(tot), "avg_duration_" + units[it]: sum(dur) / max(1, len(dur)),
+                    "source": rep.split("/")[-1] + " (ncu --set full --clock-control none, cold cache)"}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], *sys.argv[3:])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
     else:
         metrics(sys.argv[2], sys.argv[3])
