@@ -6,11 +6,12 @@ caller gets an exception.  Nothing in the product path ever imports `oracle/`.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pathlib
 import threading
 
 PKG = pathlib.Path(__file__).resolve().parent
-LIB_PATH = PKG / "libvlo_b200.so"
+LIB_PATH = pathlib.Path(os.environ.get("VLO_LIB") or PKG / "libvlo_b200.so")   # VLO_LIB: A/B a second build
 
 
 class VloError(RuntimeError):

@@ -311,15 +311,15 @@ struct AttnMergeParams {
   float scale_log2;
 };
 
+constexpr int kMergeFast = 20;  // splits handled by the register-resident fast path (one wave: <= 18)
+
 __global__ void __launch_bounds__(128) attn_merge_kernel(const AttnMergeParams p) {
-  // one block per (head, token): thread d owns one output dim.  The (max, sum) pairs of all splits are
-  // fetched in one parallel round into shared memory, turned into weights once, and the weighted sum of
-  // the partial rows then runs as independent (pipelined) loads.
+  // one block per (head, token): thread d owns one output dim.
   __shared__ float s_m[160], s_w[160];
   __shared__ float s_den;
   const int head = blockIdx.x, tok = blockIdx.y, d = threadIdx.x;
   pdl_trigger();
-  pdl_wait();
+  // the item tables were uploaded by the memcpy at the start of the step -> readable before the wait
   const AttnItem it = p.items[p.tok_item[tok]];
   const int G = p.n_heads / p.n_kv_heads;
   const int kvh = head / G, g = head % G;
@@ -328,11 +328,40 @@ __global__ void __launch_bounds__(128) attn_merge_kernel(const AttnMergeParams p
   const float c = p.scale_log2;
   const size_t slot0 = static_cast<size_t>(it.ws_slot0) + static_cast<size_t>(kvh) * it.n_splits * rows + r;
   const int ns = it.n_splits;  // <= 148
-  float l_mine = 0.f;
+  const float* o = p.ws_o + slot0 * kAttnHD + d;
+  const size_t stride = static_cast<size_t>(rows) * kAttnHD;
+  __nv_bfloat16* dst = p.out + (static_cast<size_t>(tok) * p.n_heads + head) * kAttnHD + d;
+  pdl_wait();
+  if (ns <= kMergeFast) {
+    // every thread fetches all (max, sum) pairs (broadcast loads) and its own column of all partial rows in ONE
+    // round of independent loads; weights are then computed redundantly per thread: no shared memory, no barrier.
+    float m[kMergeFast], l[kMergeFast], ov[kMergeFast];
+#pragma unroll
+    for (int s = 0; s < kMergeFast; ++s) {
+      m[s] = -INFINITY, l[s] = 0.f, ov[s] = 0.f;
+      if (s < ns) {
+        const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + (slot0 + static_cast<size_t>(s) * rows) * 2);
+        m[s] = ml.x, l[s] = ml.y;
+        ov[s] = o[s * stride];
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < kMergeFast; ++s) mx = fmaxf(mx, m[s]);
+    float den = 0.f, acc = 0.f;
+#pragma unroll
+    for (int s = 0; s < kMergeFast; ++s) {
+      const float w = (m[s] == -INFINITY) ? 0.f : exp2f((m[s] - mx) * c);
+      den += l[s] * w;
+      acc += ov[s] * w;
+    }
+    *dst = __float2bfloat16_rn(acc / den);
+    return;
+  }
+  // general path (many splits: one long sequence alone on the GPU with a tiny block budget)
   for (int s = d; s < ns; s += 128) {
     const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + (slot0 + static_cast<size_t>(s) * rows) * 2);
     s_m[s] = ml.x;
-    l_mine = ml.y;  // at most two splits per thread (ns <= 148 < 256); keep the second separately below
     s_w[s] = ml.y;
   }
   __syncthreads();
@@ -352,13 +381,10 @@ __global__ void __launch_bounds__(128) attn_merge_kernel(const AttnMergeParams p
     s_den = den;
   }
   float acc = 0.f;
-  const float* o = p.ws_o + slot0 * kAttnHD + d;
-  const size_t stride = static_cast<size_t>(rows) * kAttnHD;
 #pragma unroll 4
   for (int s = 0; s < ns; ++s) acc += o[s * stride] * s_m[s];
   __syncthreads();
-  (void)l_mine;
-  p.out[(static_cast<size_t>(tok) * p.n_heads + head) * kAttnHD + d] = __float2bfloat16_rn(acc / s_den);
+  *dst = __float2bfloat16_rn(acc / s_den);
 }
 
 }  // namespace vlo

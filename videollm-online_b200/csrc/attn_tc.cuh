@@ -10,6 +10,9 @@
 //   warp 1      MMA issuer:   S_j -> TMEM S[j&1];  after P_j is staged: O += P_j V_j      (software-pipelined: S_{j+1} first)
 //   warps 2-5   softmax:      tcgen05.ld S row -> online softmax with lazy (threshold) rescaling of O in TMEM ->
 //                             P_j as bf16 into a 128B-swizzled K-major smem tile (double buffered) -> epilogue
+//   Measured alternatives (same box, 12k keys, q = 11): two warps per lane quadrant splitting the S row (15.3 vs 15.6 us)
+//   and two ping-pong softmax groups with separate O accumulators (16.5 us) do not pay: the steady state of this
+//   kernel already streams K/V at ~5.7 TB/s; what is left is ramp (Q staging after the grid dependency) and tail.
 //   K tile: K-major B operand (same descriptor as the GEMMs).  V tile: rows = keys, d contiguous -> MN-major B operand.
 #pragma once
 #include <cuda.h>
@@ -119,6 +122,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Work item.  The item table was uploaded by a memcpy at the start of the step; a memcpy is a full stream-order
+  // dependency for the first kernel of the step, so it is complete before ANY kernel of the step runs and may be
+  // read before pdl_wait().  Issued first so its latency hides behind the barrier / TMEM set-up.
+  const AttnItem it = p.items[blockIdx.z];
   if (threadIdx.x == 0) VLO_TC_STAMP(0, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_k);
@@ -146,10 +153,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();  // after the TMEM allocation (see gemm_ws.cuh); successors may start their prologues
 
-  // Work item and split geometry.  The item table was uploaded by a memcpy at the start of the step; a memcpy is a
-  // full stream-order dependency for the first kernel of the step, so it is complete before ANY kernel of the
-  // step runs and may be read before pdl_wait().
-  const AttnItem it = p.items[blockIdx.z];
+  // split geometry
   const int split = blockIdx.x;
   const int kvh = blockIdx.y;
   const int G = p.n_heads / p.n_kv_heads;

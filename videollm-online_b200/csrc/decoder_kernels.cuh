@@ -57,6 +57,14 @@ __global__ void __launch_bounds__(1024) resid_rmsnorm_kernel(const ResidNormPara
   const int t = blockIdx.x;
   __nv_bfloat16* h = p.h + static_cast<size_t>(t) * p.H;
   pdl_trigger();
+  // Everything that does not depend on the producer kernel is fetched BEFORE the grid dependency resolves: the norm
+  // weight (a static tensor that the 15 GB weight stream has long evicted from L2 - an HBM miss that used to sit on
+  // the critical path after the block reduction), the stream-K plane count of this thread's first column group and
+  // the last-token index (tables uploaded by the memcpy at the start of the step).
+  const int i0 = threadIdx.x * 4;
+  const uint2 w_pre = (i0 < p.H) ? *reinterpret_cast<const uint2*>(p.w + i0) : make_uint2(0u, 0u);
+  const int ns_pre = (p.n_splits < 0 && i0 < p.H) ? sk_planes(i0 >> 7, p.sk) : p.n_splits;
+  const int li = p.last_index ? p.last_index[t] : -1;
   pdl_wait();
   float ss = 0.f;
   for (int i = threadIdx.x * 4; i < p.H; i += blockDim.x * 4) {
@@ -64,7 +72,7 @@ __global__ void __launch_bounds__(1024) resid_rmsnorm_kernel(const ResidNormPara
     float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw.x));
     float2 v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw.y));
     if (p.n_splits != 0) {
-      const int ns = p.n_splits > 0 ? p.n_splits : sk_planes(i >> 7, p.sk);
+      const int ns = (i == i0) ? ns_pre : (p.n_splits > 0 ? p.n_splits : sk_planes(i >> 7, p.sk));
       const float* pp = p.part + static_cast<size_t>(t) * p.H + i;
       float4 a[kFixMaxPlanes];
 #pragma unroll
@@ -89,9 +97,8 @@ __global__ void __launch_bounds__(1024) resid_rmsnorm_kernel(const ResidNormPara
   }
   const float tot = block_sum(ss, red);
   const float rstd = rsqrtf(tot / static_cast<float>(p.H) + p.eps);
-  const int li = p.last_index ? p.last_index[t] : -1;
   for (int i = threadIdx.x * 4; i < p.H; i += blockDim.x * 4) {
-    const uint2 wraw = *reinterpret_cast<const uint2*>(p.w + i);
+    const uint2 wraw = (i == i0) ? w_pre : *reinterpret_cast<const uint2*>(p.w + i);
     const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wraw.x));
     const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wraw.y));
     uint2 o;
@@ -131,21 +138,39 @@ struct QkvRopeParams {
 __global__ void __launch_bounds__(64) qkv_rope_append_kernel(const QkvRopeParams p) {
   const int t = blockIdx.x, hh = blockIdx.y, d = threadIdx.x;
   pdl_trigger();
-  pdl_wait();
+  // Before the grid dependency resolves: token position / cache row (tables uploaded by the memcpy at the start of
+  // the step), the RoPE table entries (static) and the plane count - three dependent round trips off the critical path.
   const int width = (p.n_heads + 2 * p.n_kv_heads) * 128;
   const float* pp = p.part + static_cast<size_t>(t) * width + hh * 128 + d;
-  float x1 = 0.f, x2 = 0.f;
   const int ns = p.n_splits > 0 ? p.n_splits : sk_planes(hh, p.sk);
-  for (int s = 0; s < ns; ++s) {
-    x1 += pp[s * p.split_stride];
-    x2 += pp[s * p.split_stride + 64];
+  const int pos = p.tok_pos[t];
+  const long long kvrow = p.tok_kvrow[t];
+  const bool rot = hh < p.n_heads + p.n_kv_heads;
+  const float c = rot ? __bfloat162float(p.cos_tab[static_cast<size_t>(pos) * 64 + d]) : 1.f;
+  const float s = rot ? __bfloat162float(p.sin_tab[static_cast<size_t>(pos) * 64 + d]) : 0.f;
+  pdl_wait();
+  float x1 = 0.f, x2 = 0.f;
+  if (ns <= kFixMaxPlanes) {  // all plane loads in flight together
+    float a1[kFixMaxPlanes], a2[kFixMaxPlanes];
+#pragma unroll
+    for (int k = 0; k < kFixMaxPlanes; ++k) {
+      a1[k] = (k < ns) ? pp[k * p.split_stride] : 0.f;
+      a2[k] = (k < ns) ? pp[k * p.split_stride + 64] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kFixMaxPlanes; ++k) {  // plane order: deterministic
+      x1 += a1[k];
+      x2 += a2[k];
+    }
+  } else {
+    for (int k = 0; k < ns; ++k) {
+      x1 += pp[k * p.split_stride];
+      x2 += pp[k * p.split_stride + 64];
+    }
   }
   x1 = bf16_round(x1);
   x2 = bf16_round(x2);
-  const int pos = p.tok_pos[t];
-  if (hh < p.n_heads + p.n_kv_heads) {
-    const float c = __bfloat162float(p.cos_tab[static_cast<size_t>(pos) * 64 + d]);
-    const float s = __bfloat162float(p.sin_tab[static_cast<size_t>(pos) * 64 + d]);
+  if (rot) {
     const float o1 = bf16_round(bf16_round(x1 * c) + bf16_round(-x2 * s));
     const float o2 = bf16_round(bf16_round(x2 * c) + bf16_round(x1 * s));
     x1 = o1;
@@ -157,7 +182,7 @@ __global__ void __launch_bounds__(64) qkv_rope_append_kernel(const QkvRopeParams
   } else {
     const int kvh = (hh - p.n_heads) % p.n_kv_heads;
     __nv_bfloat16* base = (hh < p.n_heads + p.n_kv_heads) ? p.k_cache : p.v_cache;
-    dst = base + (p.tok_kvrow[t] + static_cast<long long>(kvh) * p.kv_head_stride + pos) * 128;
+    dst = base + (kvrow + static_cast<long long>(kvh) * p.kv_head_stride + pos) * 128;
   }
   dst[d] = __float2bfloat16_rn(x1);
   dst[d + 64] = __float2bfloat16_rn(x2);
@@ -176,15 +201,24 @@ struct SwigluParams {
 };
 __global__ void __launch_bounds__(256) swiglu_kernel(const SwigluParams p) {
   pdl_trigger();
-  pdl_wait();
   const long long n4 = static_cast<long long>(p.T) * p.I / 4;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n4;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const long long idx0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  // index arithmetic and stream-K plane counts of the first element group: before the grid dependency resolves
+  int t0 = 0, c0 = 0, ng0 = 0, nu0 = 0;
+  if (idx0 < n4) {
+    const long long e = idx0 * 4;
+    t0 = static_cast<int>(e / p.I), c0 = static_cast<int>(e % p.I);
+    ng0 = p.n_splits > 0 ? p.n_splits : sk_planes(c0 >> 7, p.sk);
+    nu0 = p.n_splits > 0 ? p.n_splits : sk_planes((p.I + c0) >> 7, p.sk);
+  }
+  pdl_wait();
+  for (long long idx = idx0; idx < n4; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long e = idx * 4;
-    const int t = static_cast<int>(e / p.I), i = static_cast<int>(e % p.I);
+    const bool first = idx == idx0;
+    const int t = first ? t0 : static_cast<int>(e / p.I), i = first ? c0 : static_cast<int>(e % p.I);
     const float* pg = p.part + static_cast<size_t>(t) * 2 * p.I + i;
-    const int ng = p.n_splits > 0 ? p.n_splits : sk_planes(i >> 7, p.sk);
-    const int nu = p.n_splits > 0 ? p.n_splits : sk_planes((p.I + i) >> 7, p.sk);
+    const int ng = first ? ng0 : (p.n_splits > 0 ? p.n_splits : sk_planes(i >> 7, p.sk));
+    const int nu = first ? nu0 : (p.n_splits > 0 ? p.n_splits : sk_planes((p.I + i) >> 7, p.sk));
     float4 ga[kFixMaxPlanes], ua[kFixMaxPlanes];
 #pragma unroll
     for (int s = 0; s < kFixMaxPlanes; ++s) {
