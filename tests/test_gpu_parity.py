@@ -307,3 +307,45 @@ def test_multistream_scheduler_equals_independent_liveinfer(built, golden, tiny)
         assert got == want, (s, got, want)
         model.engine.stream_close(sess.stream_id)
     assert sched.frames_done == 15
+
+
+def test_full_width_layers_at_12k_context():
+    """BASELINE.json configs[1] shapes: Llama-3-8B width (hidden 4096, 32/8 heads, MLP 14336, vocab 128256), a
+    12 000-token cache and one frame step (q = 11), on a 2-layer stack so that the CPU oracle finishes in seconds.
+    Covers what the tiny goldens cannot: the stream-K schedule of the real weight shapes, the split-KV plan at 12k
+    keys, RoPE positions past max_position_embeddings = 8192, the 1 GB lm_head."""
+    import vlo_oracle as O
+    from videollm_online_b200 import llama3_8b_siglip_l, weights as W
+    from videollm_online_b200.modeling_live import build_live
+    cfg = llama3_8b_siglip_l()
+    cfg.num_hidden_layers = 2
+    llm = W.synthetic_llm_state(cfg, seed=3)
+    llm["lm_head.weight"] = (llm["lm_head.weight"].float() * 8).to(torch.bfloat16)
+    N, q = 12000, 11
+    model, _ = build_live(config=cfg, llm_state=llm, set_vision_inside=False, device="cuda:0", max_streams=1,
+                          max_kv_tokens=N + 256, max_step_tokens=128, max_vit_batch=1)
+    eng = model.engine
+    kv = model.new_stream()
+    eng.kv_fill_synthetic(kv.stream_id, N, seed=5)
+    cache = O.KVCache(cfg.num_hidden_layers)
+    for layer in range(cfg.num_hidden_layers):
+        cache.update(layer, eng.kv_read(kv.stream_id, layer, False).cpu()[None], eng.kv_read(kv.stream_id, layer, True).cpu()[None])
+    g = torch.Generator().manual_seed(11)
+    emb = (torch.randn(q, cfg.hidden_size, generator=g) * 0.5).to(torch.bfloat16)
+    out = model(inputs_embeds=emb[None].cuda(), past_key_values=kv, use_cache=True)
+    allpos = eng.last_step_logits(q)
+    ref = O.llama_forward(llm, cfg, emb, cache)          # [q, V]; appends the q new K/V rows to `cache`
+    assert kv.get_seq_length() == N + q == cache.get_seq_length()
+    mx, frac = _close(out.logits[0, 0], ref[-1], LOGIT_ATOL, LOGIT_RTOL)
+    assert frac == 0.0, f"last-position logits max err {mx}"
+    mx, frac = _close(allpos, ref, LOGIT_ATOL, LOGIT_RTOL)
+    assert frac == 0.0, f"all-position logits max err {mx}"
+    top2 = ref[-1].float().topk(2).values
+    if float(top2[0] - top2[1]) > 2 * LOGIT_ATOL:
+        assert eng.read_decisions(1)[0].argmax_id == int(ref[-1].float().argmax())
+    for layer in range(cfg.num_hidden_layers):           # the rows appended at positions 12000..12010 (RoPE past 8192)
+        k = eng.kv_read(kv.stream_id, layer, False)[:, N:]
+        v = eng.kv_read(kv.stream_id, layer, True)[:, N:]
+        assert _close(k, cache.k[layer][0, :, N:], 4e-2, 2e-2)[1] == 0.0
+        assert _close(v, cache.v[layer][0, :, N:], 4e-2, 2e-2)[1] == 0.0
+    eng.stream_close(kv.stream_id)

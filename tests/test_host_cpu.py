@@ -168,3 +168,53 @@ def test_bench_reference_arm_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_checkpoint_directory_loader_roundtrip(tmp_path):
+    """base-model safetensors shards + a PEFT adapter directory (LoRA A/B on the Linear layers the
+    reference targets, `modules_to_save=['connector']`, both saved-key spellings) + a SigLIP directory, read by the
+    same code path `build_live(llm_pretrained=..., resume_from_checkpoint=...)` uses, equal the in-memory packing."""
+    from safetensors.torch import save_file
+    from videollm_online_b200 import tiny_config, weights as W
+    from videollm_online_b200.modeling_live import _load_checkpoints
+    cfg = tiny_config()
+    full, vs = W.synthetic_llm_state(cfg, seed=4), W.synthetic_vision_state(cfg, seed=5)
+    base = {k: v for k, v in full.items() if not k.startswith("connector.")}     # the base LLM has no connector
+    keys = sorted(base)
+    llm_dir, ad_dir, vis_dir = tmp_path / "llm", tmp_path / "adapter", tmp_path / "siglip"
+    for d in (llm_dir, ad_dir, vis_dir):
+        d.mkdir()
+    save_file({k: base[k].contiguous() for k in keys[: len(keys) // 2]}, str(llm_dir / "model-00001-of-00002.safetensors"))
+    save_file({k: base[k].contiguous() for k in keys[len(keys) // 2:]}, str(llm_dir / "model-00002-of-00002.safetensors"))
+    g = torch.Generator().manual_seed(9)
+    r, alpha = 8, 16
+    adapter = {}
+    for i in range(cfg.num_hidden_layers):
+        for j, name in enumerate(("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj",
+                                  "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj")):
+            w = base[f"model.layers.{i}.{name}.weight"]
+            infix = ".default" if (i + j) % 2 else ""        # PEFT state_dict() vs saved-adapter spelling
+            adapter[f"base_model.model.model.layers.{i}.{name}.lora_A{infix}.weight"] = (torch.randn(r, w.shape[1], generator=g) * 0.05).bfloat16()
+            adapter[f"base_model.model.model.layers.{i}.{name}.lora_B{infix}.weight"] = (torch.randn(w.shape[0], r, generator=g) * 0.05).bfloat16()
+    adapter["base_model.model.lm_head.lora_A.weight"] = (torch.randn(r, cfg.hidden_size, generator=g) * 0.05).bfloat16()
+    adapter["base_model.model.lm_head.lora_B.weight"] = (torch.randn(cfg.vocab_size, r, generator=g) * 0.05).bfloat16()
+    for k in ("connector.0.weight", "connector.0.bias", "connector.2.weight", "connector.2.bias"):
+        adapter["base_model.model." + k] = full[k].contiguous()
+    save_file(adapter, str(ad_dir / "adapter_model.safetensors"))
+    save_file({"vision_model." + k: v.contiguous() for k, v in vs.items()} | {"text_model.unused": torch.zeros(3)},
+              str(vis_dir / "model.safetensors"))
+    cfg.vision_pretrained = str(vis_dir)
+    got = _load_checkpoints(cfg, str(llm_dir), str(ad_dir), True, "cpu", 256, r, alpha)
+    want = W.pack_llm_for_engine(cfg, W.merge_lora(dict(base), adapter, lora_alpha=alpha, lora_r=r), "cpu", 256)
+    want.update(W.pack_vision_for_engine(cfg, vs, "cpu"))
+    assert set(got) == set(want)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    # the adapter really changed the weights, and the connector came from the adapter
+    assert not torch.equal(got["L0.qkv"], W.pack_llm_for_engine(cfg, full, "cpu", 256)["L0.qkv"])
+    assert torch.equal(got["conn.0.w"], full["connector.0.weight"])
+    assert not torch.equal(got["lm_head"], full["lm_head.weight"])         # lora_modules ends with |lm_head$ (models/arguments_live.py:16)
+    # missing directory: loud failure, no silent random init (the reference only warns, models/modeling_live.py:218)
+    from videollm_online_b200._lib import VloError
+    with pytest.raises(VloError):
+        _load_checkpoints(cfg, str(tmp_path / "nope"), "", False, "cpu", 256, r, alpha)

@@ -9,7 +9,7 @@ timeout 700 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-n
 echo "launch list rc=$?"
 # the decoder weight-streaming GEMM (qkv, o, gate|up, down of consecutive layers)
 timeout 700 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k "regex:vlo::gemm_ws_kernel<1, 16" -s 430 -c 8 -o gpurun_out/prof_gemm_ws_${TAG} $B > gpurun_out/ncu_gemm.log 2>&1
+    -k "regex:gemm_ws_kernel<.int.1, .int.16" -s 430 -c 8 -o gpurun_out/prof_gemm_ws_${TAG} $B > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm_ws rc=$?"
 # the KV-append attention kernel
 timeout 700 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
