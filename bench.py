@@ -272,8 +272,11 @@ def run_engine_arm(args):
     fes = [None, None]
     fbufs = [torch.empty(1, 3, S, S, dtype=torch.uint8, device=dev) for _ in range(2)]
 
-    def encode_on_side(i, slot, from_host):
-        side.wait_stream(stream)
+    def encode_on_side(i, slot, from_host, after=None):
+        if after is not None:
+            side.wait_event(after)      # frame i arrives while the step launched just before `after` is running
+        else:
+            side.wait_stream(stream)
         with torch.cuda.stream(side):
             if from_host:   # e2e: this step's input comes from pinned host memory
                 fbufs[slot].copy_(frames_host[i:i + 1], non_blocking=True)
@@ -282,16 +285,21 @@ def run_engine_arm(args):
                 fes[slot] = eng.vit_encode(frames_dev[i:i + 1])
             evs[slot].record(side)
 
+    pre_evs = [torch.cuda.Event(), torch.cuda.Event()]
+
     def pipelined(n, base, from_host=False, read_back=False):
         encode_on_side(base, 0, from_host)
         for i in range(n):
-            if i + 1 < n:
-                encode_on_side(base + i + 1, (i + 1) & 1, from_host)
             stream.wait_event(evs[i & 1])
             fe = fes[i & 1]
             fe.record_stream(stream)
             packed[1:] = fe
+            pre_evs[i & 1].record(stream)
+            # the decoder step is enqueued FIRST: after a decision read-back the host is the critical path, and the
+            # ~100 launches of the next frame's ViT must not sit in front of the step's
             eng.step([sid], [11], packed, row_ids=prefix, want_logits=True)
+            if i + 1 < n:
+                encode_on_side(base + i + 1, (i + 1) & 1, from_host, after=pre_evs[i & 1])
             if read_back:
                 eng.read_decisions(1)
 

@@ -147,8 +147,12 @@ cnt = torch.tensor([len(mine)]); dist.all_reduce(cnt); assert int(cnt) == 5
 print('rank', dist.get_rank(), 'ok')
 """)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    import socket
+    with socket.socket() as so:          # a free rendezvous port (a fixed one can still be in TIME_WAIT from the last run)
+        so.bind(("127.0.0.1", 0))
+        port = so.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29631", str(script)], capture_output=True, text=True, env=env, timeout=170)
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=env, timeout=170)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
 

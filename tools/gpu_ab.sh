@@ -12,7 +12,7 @@ for line in sys.stdin:
     except Exception: continue
     ra = d.get('roofline_attn', {})
     print('$lib', 'value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'seq', d['config'].get('sequential_fps'),
-          'attn_pair_us', ra.get('avg_us_per_launch'), 'frac', round(ra.get('frac',0),3), 'main', ra.get('main_kernel_only'), 'extras', json.dumps(d.get('extras', {}))[:300])
+          'attn_pair_us', ra.get('avg_us_per_launch'), 'frac', round(ra.get('frac',0),3), 'main', ra.get('main_kernel_only'), 'attn8', (d.get('extras') or {}).get('attn_kvappend_8streams', {}).get('us_per_launch_incl_merge'), 'ar', (d.get('extras') or {}).get('ar_decode', {}).get('tokens_per_s'), 'ms8', (d.get('extras') or {}).get('multistream8', {}).get('frames_per_s'))
 "
   done
 done

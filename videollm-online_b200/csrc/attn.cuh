@@ -313,6 +313,34 @@ struct AttnMergeParams {
 
 constexpr int kMergeFast = 20;  // splits handled by the register-resident fast path (one wave: <= 18)
 
+// Every thread fetches all (max, sum) pairs (broadcast loads) and its own column of all partial rows in ONE round
+// of independent loads; weights are then computed redundantly per thread: no shared memory, no barrier.
+template <int MAXS>
+__device__ __forceinline__ float attn_merge_regs(const float* ws_ml, const float* o, size_t slot0, int rows, size_t stride,
+                                                 int ns, float c) {
+  float m[MAXS], l[MAXS], ov[MAXS];
+#pragma unroll
+  for (int s = 0; s < MAXS; ++s) {
+    m[s] = -INFINITY, l[s] = 0.f, ov[s] = 0.f;
+    if (s < ns) {
+      const float2 ml = *reinterpret_cast<const float2*>(ws_ml + (slot0 + static_cast<size_t>(s) * rows) * 2);
+      m[s] = ml.x, l[s] = ml.y;
+      ov[s] = o[s * stride];
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < MAXS; ++s) mx = fmaxf(mx, m[s]);
+  float den = 0.f, acc = 0.f;
+#pragma unroll
+  for (int s = 0; s < MAXS; ++s) {
+    const float w = (m[s] == -INFINITY) ? 0.f : exp2f((m[s] - mx) * c);
+    den += l[s] * w;
+    acc += ov[s] * w;
+  }
+  return acc / den;
+}
+
 __global__ void __launch_bounds__(128) attn_merge_kernel(const AttnMergeParams p) {
   // one block per (head, token): thread d owns one output dim.
   __shared__ float s_m[160], s_w[160];
@@ -332,30 +360,12 @@ __global__ void __launch_bounds__(128) attn_merge_kernel(const AttnMergeParams p
   const size_t stride = static_cast<size_t>(rows) * kAttnHD;
   __nv_bfloat16* dst = p.out + (static_cast<size_t>(tok) * p.n_heads + head) * kAttnHD + d;
   pdl_wait();
+  if (ns <= 4) {   // many sequences per step (8 streams -> 2 splits each): keep the unrolled work proportional
+    *dst = __float2bfloat16_rn(attn_merge_regs<4>(p.ws_ml, o, slot0, rows, stride, ns, c));
+    return;
+  }
   if (ns <= kMergeFast) {
-    // every thread fetches all (max, sum) pairs (broadcast loads) and its own column of all partial rows in ONE
-    // round of independent loads; weights are then computed redundantly per thread: no shared memory, no barrier.
-    float m[kMergeFast], l[kMergeFast], ov[kMergeFast];
-#pragma unroll
-    for (int s = 0; s < kMergeFast; ++s) {
-      m[s] = -INFINITY, l[s] = 0.f, ov[s] = 0.f;
-      if (s < ns) {
-        const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + (slot0 + static_cast<size_t>(s) * rows) * 2);
-        m[s] = ml.x, l[s] = ml.y;
-        ov[s] = o[s * stride];
-      }
-    }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int s = 0; s < kMergeFast; ++s) mx = fmaxf(mx, m[s]);
-    float den = 0.f, acc = 0.f;
-#pragma unroll
-    for (int s = 0; s < kMergeFast; ++s) {
-      const float w = (m[s] == -INFINITY) ? 0.f : exp2f((m[s] - mx) * c);
-      den += l[s] * w;
-      acc += ov[s] * w;
-    }
-    *dst = __float2bfloat16_rn(acc / den);
+    *dst = __float2bfloat16_rn(attn_merge_regs<kMergeFast>(p.ws_ml, o, slot0, rows, stride, ns, c));
     return;
   }
   // general path (many splits: one long sequence alone on the GPU with a tiny block budget)

@@ -64,6 +64,7 @@ class LiveInfer:
         self.prefetch_next = True
         self._side = torch.cuda.Stream(self.device)
         self._prefetched = None   # (frame_idx, embeds tensor, event)
+        self._want_prefetch = None  # frame index to encode ahead right after the next decoder step is enqueued
         self.reset()
 
     # ------------------------------------------------------------------ session control
@@ -76,7 +77,10 @@ class LiveInfer:
         self.last_ids = torch.tensor([[]], dtype=torch.long)
         self._kv.engine.stream_reset(self._kv.stream_id)
         self.past_key_values = None
+        if getattr(self, "_prefetched", None) is not None:   # an encode-ahead in flight owns the ViT workspaces
+            torch.cuda.current_stream(self.device).wait_event(self._prefetched[2])
         self._prefetched = None
+        self._want_prefetch = None
 
     def load_video(self, video_path_or_tensor):
         """Reference: read_video(...)[0].to('cuda') (demo/inference.py:111-115).  Accepts a uint8
@@ -109,18 +113,15 @@ class LiveInfer:
                 pe.record_stream(main)
                 embeds.append(pe)
                 start += 1
+            elif self._prefetched is not None:
+                main.wait_event(self._prefetched[2])   # a stale encode-ahead still owns the engine's ViT workspaces
             self._prefetched = None
             if start < ranger.stop:
                 embeds.extend(self.model.visual_embed(self.video_tensor[start:ranger.stop]).split(self.frame_num_tokens))
             self.frame_embeds_queue.extend([(r / self.frame_fps, e) for r, e in zip(ranger, embeds)])
             nxt = frame_idx + 1
-            if self.prefetch_next and self.video_tensor is not None and nxt < self.video_tensor.size(0):
-                self._side.wait_stream(main)
-                with torch.cuda.stream(self._side):
-                    pe = self.model.visual_embed(self.video_tensor[nxt:nxt + 1])
-                    ev = torch.cuda.Event()
-                    ev.record(self._side)
-                self._prefetched = (nxt, pe, ev)
+            self._want_prefetch = nxt if (self.prefetch_next and self.video_tensor is not None
+                                          and nxt < self.video_tensor.size(0)) else None
         self.last_frame_idx = frame_idx
         self.video_time = video_time
 
@@ -135,8 +136,23 @@ class LiveInfer:
         if n_fr:
             packed[n_ids:] = frame_embeds.view(-1, self.hidden_size)
         row_ids = torch.cat([ids, torch.full((n_fr,), -1, dtype=torch.int64)]).to(self.device, non_blocking=True)
+        main = torch.cuda.current_stream(self.device)
+        pre = None
+        if self._want_prefetch is not None:
+            pre = torch.cuda.Event()
+            pre.record(main)
         eng.step([self._kv.stream_id], [n_ids + n_fr], packed, row_ids=row_ids)   # token rows gathered on the device
         self.past_key_values = self._kv
+        if pre is not None:
+            # encode-ahead of the next frame, enqueued AFTER the step's launches (the host is the critical path right
+            # after a decision read-back) but ordered only behind what preceded the step: it runs concurrently with it
+            nxt, self._want_prefetch = self._want_prefetch, None
+            self._side.wait_event(pre)
+            with torch.cuda.stream(self._side):
+                pe = self.model.visual_embed(self.video_tensor[nxt:nxt + 1])
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            self._prefetched = (nxt, pe, ev)
         dec = eng.read_decisions(1)[0]
         if self.decision_hook is not None:
             dec = self.decision_hook(dec, self._n_calls)
