@@ -109,6 +109,13 @@ def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 4, vit_laye
     head, pool) and the full-width decoder truncated to `dec_layers` of 32 layers over a 12k-token cache
     (+ final norm, lm_head), each scaled to the full layer count -> seconds per full frame step."""
     import torch
+    # all the host threads it can use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would time the CPU arm
+    # on one core; use one thread per physical core (torch's own default outside torchrun)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(max(torch.get_num_threads(), max(1, avail // 2)))
     sys.path.insert(0, str(ROOT / "oracle"))
     import vlo_bootstrap  # noqa: F401
     import vlo_oracle as O
