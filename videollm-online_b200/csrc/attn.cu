@@ -150,9 +150,10 @@ static int launch_merge(const AttnPlan& plan, void* d_out, int n_heads, int n_kv
 
 static int attn_run_tc(const AttnPlan& plan, const void* d_q, const void* d_k, const void* d_v, long long kv_rows,
                        void* d_out, int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream) {
-  CUtensorMap tk, tv;
+  CUtensorMap tk, tv, tq;
   if (tmap_2d_sw128(d_k, static_cast<int>(kv_rows), kAttnHD, kTcBlk, 1, &tk) != 0) return -1;
   if (tmap_2d_sw128(d_v, static_cast<int>(kv_rows), kAttnHD, kTcBlk, 1, &tv) != 0) return -1;
+  if (tmap_q3d_sw128(d_q, plan.total_tokens, n_heads, n_heads / n_kv_heads, &tq) != 0) return -1;
   static bool attr_set = false;
   if (!attr_set) {
     VLO_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
@@ -191,7 +192,7 @@ static int attn_run_tc(const AttnPlan& plan, const void* d_q, const void* d_k, c
   p.v_sbo = swap_ls ? static_cast<uint32_t>(kTcSub) : 1024u;
   prof_begin(PROF_ATTN, stream, plan.algo_bytes);
   VLO_CUDA(launch_pdl(attn_tc_kernel, dim3(plan.max_splits, n_kv_heads, plan.n_items), dim3(kTcThreads), kTcSmemBytes, stream,
-                      tk, tv, p));
+                      tk, tv, tq, p));
   prof_end(stream);
   count_launch();
   if (plan.skip_merge) return 0;

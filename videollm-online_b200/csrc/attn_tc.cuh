@@ -3,10 +3,12 @@
 //
 //   S = Q K^T and O += P V run on the 5th-gen tensor cores (tcgen05.mma, M = 128, N = 128, fp32 accumulators in
 //   TMEM), so K and V are read from shared memory exactly once by the MMA unit instead of 3-4x through ldmatrix.
-//   The <= 128/G query tokens x G heads of a kv head occupy TMEM lanes  lane = g * (128/G) + t,  one softmax
-//   thread per lane: row max / exp2 / row sum need no shuffles.
+//   The <= 128/G query tokens x G heads of a kv head occupy TMEM lanes  lane = t * G + g  (dense: the same row
+//   order as the partial workspace), one softmax thread per lane: row max / exp2 / row sum need no shuffles; warps
+//   whose 32 lanes hold no query row skip the softmax arithmetic.  The Q tile is ONE 3-D TMA box per 64-d half
+//   (tmap_q3d_sw128), issued by the producer as soon as the grid dependency resolves.
 //
-//   warp 0      TMA producer: per 128-key block one stage = K [128 keys x 128 d] + V [128 keys x 128 d] (64 KB), 2 stages
+//   warp 0      TMA producer: Q tile, then per 128-key block one stage = K [128 keys x 128 d] + V [128 keys x 128 d] (64 KB), 2 stages
 //   warp 1      MMA issuer:   S_j -> TMEM S[j&1];  after P_j is staged: O += P_j V_j      (software-pipelined: S_{j+1} first)
 //   warps 2-5   softmax:      tcgen05.ld S row -> online softmax with lazy (threshold) rescaling of O in TMEM ->
 //                             P_j as bf16 into a 128B-swizzled K-major smem tile (double buffered) -> epilogue
@@ -101,7 +103,8 @@ __device__ __forceinline__ uint32_t tc_sw_off(int r, int c16) {
 
 // grid = (max_splits, n_kv_heads, n_items); block = 192.
 __global__ void __launch_bounds__(kTcThreads, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnTcParams pp) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+               const __grid_constant__ CUtensorMap tm_q, const AttnTcParams pp) {
   const AttnParams& p = pp.base;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -130,6 +133,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_q);
     for (int i = 0; i < kTcStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -143,7 +147,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_done, 1);
-    mbar_init(q_ready, 128);
+    mbar_init(q_ready, 1);   // TMA transaction barrier
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -157,7 +161,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
   const int split = blockIdx.x;
   const int kvh = blockIdx.y;
   const int G = p.n_heads / p.n_kv_heads;
-  const int rph = 128 / G;  // TMEM lanes (rows) per query head
   const int kv_end = it.q_pos0 + it.q_count;
   const int nblk_total = (kv_end + kTcBlk - 1) / kTcBlk;
   const int blk0 = split * it.blocks_per_split;
@@ -191,6 +194,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
     if (warp == 0) {
       if (lane == 0) {
         // ------------------------------------------------------------ TMA producer
+        // Q rows of this kv head (written by the predecessor kernel): two 16 KB boxes, rows = token * G + head
+        mbar_arrive_expect_tx(q_ready, kTcQBytes);
+        tma_load_3d(q_tile, &tm_q, q_ready, 0, kvh * G, it.q_tok0, kEvictNormal);
+        tma_load_3d(q_tile + kTcSub, &tm_q, q_ready, 64, kvh * G, it.q_tok0, kEvictNormal);
         for (int j = pre; j < nblk; ++j) {
           const int s = j % kTcStages;
           const uint32_t ph = (j / kTcStages) & 1;
@@ -259,25 +266,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
     } else {
       // -------------------------------------------------------------- softmax / correction / epilogue warps
       const int q = warp & 3;
-      const int r = q * 32 + lane;       // TMEM lane == tile row
-      const int g = r / rph, t = r % rph;
-      const bool valid = (g < G) && (t < it.q_count);
-      const int lim = valid ? it.q_pos0 + t : -1;  // last visible key (causal with offset)
+      const int r = q * 32 + lane;       // TMEM lane == tile row == t * G + g
+      const int t = r / G;
+      const bool valid = r < it.q_count * G;
+      const bool warp_live = q * 32 < it.q_count * G;   // any query row in this warp's 32 lanes?
+      const int lim = valid ? it.q_pos0 + t : -1;       // last visible key (causal with offset)
       const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-      // ---- stage Q: this thread's row, 16 chunks of 16 B, swizzled K-major; invalid rows are zero
-      {
-        const uint4* src = valid ? reinterpret_cast<const uint4*>(
-                                       p.q + (static_cast<size_t>(it.q_tok0 + t) * p.n_heads + kvh * G + g) * kAttnHD)
-                                 : nullptr;
-#pragma unroll
-        for (int c16 = 0; c16 < 16; ++c16) {
-          const uint4 v = valid ? __ldg(src + c16) : make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(q_tile + tc_sw_off(r, c16)) = v;
-        }
-        fence_proxy_async();
-        mbar_arrive(q_ready);
-        if (r == 0) VLO_TC_STAMP(2, 0);
-      }
       const float c = p.scale_log2;
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nblk; ++j) {
@@ -285,6 +279,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         mbar_wait(&s_full[b], (j >> 1) & 1);
         tc_fence_after();
         if (r == 0) VLO_TC_STAMP(2, 4 + 4 * j);
+        if (!warp_live) {  // no query row in these lanes: only keep the barrier protocol going (P/O rows stay garbage,
+                           // they feed nothing but their own discarded O rows)
+          tc_fence_before();
+          mbar_arrive(&s_empty[b]);
+          mbar_wait(&p_empty[b], ((j >> 1) & 1) ^ 1);
+          fence_proxy_async();
+          mbar_arrive(&p_full[b]);
+          continue;
+        }
         const int key0 = (blk0 + j) * kTcBlk;
         const bool need_mask = key0 + kTcBlk - 1 > it.q_pos0;  // block reaches past the first query's limit
         // S row -> registers (128 fp32), masked, row max
@@ -370,24 +373,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
       tc_fence_after();
       if (r == 0) VLO_TC_STAMP(2, 1);
       const int rows = it.q_count * G;
-      const int rr = t * G + g;  // row index inside the item, same convention as v1 / the merge kernel
-      const size_t slot = static_cast<size_t>(it.ws_slot0) + (static_cast<size_t>(kvh) * it.n_splits + split) * rows + rr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tO + lane_addr + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(p.ws_o + slot * kAttnHD + c0);
+      const size_t slot = static_cast<size_t>(it.ws_slot0) + (static_cast<size_t>(kvh) * it.n_splits + split) * rows + r;
+      if (warp_live) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                 __uint_as_float(v[4 * i + 3]));
+        for (int c0 = 0; c0 < 128; c0 += 64) {   // two 64-column reads in flight, then the stores
+          uint32_t v0[32], v1[32];
+          tmem_ld_x32(tO + lane_addr + c0, v0);
+          tmem_ld_x32(tO + lane_addr + c0 + 32, v1);
+          tmem_ld_wait();
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(p.ws_o + slot * kAttnHD + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dst[i] = make_float4(__uint_as_float(v0[4 * i]), __uint_as_float(v0[4 * i + 1]), __uint_as_float(v0[4 * i + 2]),
+                                   __uint_as_float(v0[4 * i + 3]));
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dst[8 + i] = make_float4(__uint_as_float(v1[4 * i]), __uint_as_float(v1[4 * i + 1]), __uint_as_float(v1[4 * i + 2]),
+                                       __uint_as_float(v1[4 * i + 3]));
+          }
         }
-      }
-      if (valid) {
-        p.ws_ml[slot * 2] = m_ref;
-        p.ws_ml[slot * 2 + 1] = l_run;
+        if (valid) {
+          p.ws_ml[slot * 2] = m_ref;
+          p.ws_ml[slot * 2 + 1] = l_run;
+        }
       }
       if (r == 0) VLO_TC_STAMP(2, 2);
       tc_fence_before();

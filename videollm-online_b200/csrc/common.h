@@ -153,5 +153,6 @@ int attn_run(const AttnPlan& plan, const void* d_q, const void* d_k, const void*
 
 // 2D TMA map over a row-major 16-bit matrix [rows, k], box 64 x box_rows, 128-byte swizzle (cached).
 int tmap_2d_sw128(const void* ptr, int rows, int k, int box_rows, int fmt, CUtensorMap* out);
+int tmap_q3d_sw128(const void* ptr, int n_tok, int n_heads, int G, CUtensorMap* out);  // attention Q tile (see gemm.cu)
 
 }  // namespace vlo

@@ -112,6 +112,40 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& arg
 
 }  // namespace
 
+// Query tensor [n_tok][n_heads][128] bf16 as a 3-D map; one box = (64 dims, G heads of one kv head, 128/G tokens)
+// lands in shared memory as 128 rows of 128 B ordered row = token * G + head: the K-major SW128 A tile of the
+// attention kernel.  Tokens past n_tok are zero-filled by the TMA unit.
+int tmap_q3d_sw128(const void* ptr, int n_tok, int n_heads, int G, CUtensorMap* out) {
+  TmapKey key{ptr, n_tok, n_heads, -G, 3};
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeFn enc = get_encode();
+  if (enc == nullptr) return fail("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail("TMA operand not 16-byte aligned");
+  if (G < 1 || 128 % G != 0 || n_heads % G != 0) return fail("tmap_q3d: GQA group must divide 128 and n_heads");
+  cuuint64_t dims[3] = {128, static_cast<cuuint64_t>(n_heads), static_cast<cuuint64_t>(n_tok)};
+  cuuint64_t strides[2] = {256, static_cast<cuuint64_t>(n_heads) * 256};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(G), static_cast<cuuint32_t>(128 / G)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (Q, 3-D) failed, CUresult " + std::to_string(r));
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    g_tmaps.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
 int tmap_2d_sw128(const void* ptr, int rows, int k, int box_rows, int fmt, CUtensorMap* out) {
   return get_tmap(ptr, rows, k, box_rows, fmt, out);
 }
