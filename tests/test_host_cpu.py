@@ -222,3 +222,41 @@ def test_checkpoint_directory_loader_roundtrip(tmp_path):
     from videollm_online_b200._lib import VloError
     with pytest.raises(VloError):
         _load_checkpoints(cfg, str(tmp_path / "nope"), "", False, "cpu", 256, r, alpha)
+
+
+def test_video_ingest_matches_ffmpeg_once_geometry(tmp_path):
+    """decode + `-r fps` + scale/pad of data/utils.py:51-66, restated with OpenCV (no ffmpeg here)."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    from videollm_online_b200.video_ingest import letterbox_geometry, read_video_resampled, resample_indices
+    # geometry of the filter chain: longer side -> R, shorter side even, centred
+    assert letterbox_geometry(640, 360, 384) == (384, 216, 0, 84)
+    assert letterbox_geometry(360, 640, 384) == (216, 384, 84, 0)
+    assert letterbox_geometry(500, 500, 384) == (384, 384, 0, 0)
+    assert letterbox_geometry(1280, 718, 384)[1] % 2 == 0
+    # 30 fps -> 2 fps: output k shows the source frame nearest to k / 2 s
+    assert resample_indices(60, 30.0, 2) == [0, 15, 30, 45]
+    assert resample_indices(0, 30.0, 2) == [] and resample_indices(10, 30.0, 2) == [0]
+    path = str(tmp_path / "clip.avi")
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (640, 360))
+    if not w.isOpened():
+        pytest.skip("no MJPG encoder in this OpenCV build")
+    for i in range(60):
+        f = np.full((360, 640, 3), 40, np.uint8)
+        f[100:200, 8 * i:8 * i + 100] = (0, 0, 255)      # a red (BGR) square moving right, 8 px per source frame
+        w.write(f)
+    w.release()
+    v = read_video_resampled(path, fps=2, resolution=384)
+    assert v.dtype == torch.uint8 and tuple(v.shape) == (4, 3, 384, 384)
+    assert int(v[:, :, :84].max()) == 0 and int(v[:, :, 300:].max()) == 0     # black bars above and below
+    assert int(v[:, :, 84:300].float().mean()) > 20                            # picture in the middle band
+    for k, src in enumerate((0, 15, 30, 45)):                                  # the square sits where source frame `src` had it
+        red = v[k, 0, 84:300].float() - v[k, 2, 84:300].float()                # RGB order: R - B
+        cols = (red.mean(0) > 60).nonzero().flatten()
+        centre = float(cols.float().mean())
+        want = (8 * src + 50) * 384 / 640
+        assert abs(centre - want) < 4, (k, centre, want)
+    raw = read_video_resampled(path)                                            # no resampling requested: every frame, native size
+    assert tuple(raw.shape) == (60, 3, 360, 640)
+    with pytest.raises(RuntimeError):
+        read_video_resampled(str(tmp_path / "missing.mp4"))

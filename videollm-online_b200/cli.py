@@ -1,6 +1,6 @@
 """Headless driver + FPS measurement: the engine-backed counterpart of demo/cli.py:12-50.
 
-    python -m videollm_online_b200.cli --synthetic_weights true [--frames 100]
+    python -m videollm_online_b200.cli --synthetic_weights true [--frames 100] [--video clip.mp4]
 
 Loads (or synthesises) a clip, asks for narration at t=0 and runs N iterations of
 (encode 1 frame -> KV-append step -> maybe respond), reporting the reference's
@@ -54,7 +54,9 @@ def main(liveinfer: LiveInfer, video=None, n_iters: int = 100, save_history_path
 
 
 if __name__ == '__main__':
-    n = 100
+    n, video = 100, None
     if '--frames' in sys.argv:
         n = int(sys.argv[sys.argv.index('--frames') + 1])
-    main(LiveInfer(parse_args()), n_iters=n)
+    if '--video' in sys.argv:   # a clip on disk: resampled to frame_fps and letterboxed to frame_resolution on load
+        video = sys.argv[sys.argv.index('--video') + 1]
+    main(LiveInfer(parse_args()), video=video, n_iters=n)

@@ -88,7 +88,7 @@ class LiveInfer:
         if isinstance(video_path_or_tensor, torch.Tensor):
             vt = video_path_or_tensor
         else:
-            vt = _read_video_tchw(video_path_or_tensor)
+            vt = _read_video_tchw(video_path_or_tensor, fps=self.frame_fps, resolution=self.frame_resolution)
         self.video_tensor = vt.to(self.device)
         self.num_video_frames = self.video_tensor.size(0)
         self.video_duration = self.video_tensor.size(0) / self.frame_fps
@@ -214,19 +214,7 @@ class LiveInfer:
         return query, response
 
 
-def _read_video_tchw(path: str) -> torch.Tensor:
-    try:
-        import cv2
-    except Exception as e:  # pragma: no cover
-        raise RuntimeError(f"no video decoder available for {path}: {e}")
-    cap = cv2.VideoCapture(path)
-    frames = []
-    while True:
-        ok, fr = cap.read()
-        if not ok:
-            break
-        frames.append(torch.from_numpy(cv2.cvtColor(fr, cv2.COLOR_BGR2RGB)).permute(2, 0, 1))
-    cap.release()
-    if not frames:
-        raise RuntimeError(f"could not decode any frame from {path}")
-    return torch.stack(frames)
+def _read_video_tchw(path: str, fps=None, resolution=None) -> torch.Tensor:
+    """demo/inference.py:111-115 + the preprocessing demo/cli.py:15-20 does before it (see video_ingest.py)."""
+    from .video_ingest import read_video_resampled
+    return read_video_resampled(path, fps=fps, resolution=resolution)
