@@ -144,7 +144,7 @@ assert set(got) == set(full) and all(torch.equal(got[k], full[k]) for k in full)
 # static stream -> rank assignment: round-robin, every stream owned by exactly one rank
 streams = list(range(5)); mine = [s for s in streams if s % dist.get_world_size() == dist.get_rank()]
 cnt = torch.tensor([len(mine)]); dist.all_reduce(cnt); assert int(cnt) == 5
-print('rank', dist.get_rank(), 'ok')
+sys.stdout.write('rank %d ok\\n' % dist.get_rank()); sys.stdout.flush()   # one write per rank: the two ranks share the pipe
 """)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     import socket
