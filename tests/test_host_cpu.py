@@ -260,3 +260,48 @@ def test_video_ingest_matches_ffmpeg_once_geometry(tmp_path):
     assert tuple(raw.shape) == (60, 3, 360, 640)
     with pytest.raises(RuntimeError):
         read_video_resampled(str(tmp_path / "missing.mp4"))
+
+
+def test_offline_encode_directory_layout_and_sharding(tmp_path, tiny):
+    """the host loop of distributed_encode (data/utils.py:86-104) - clip -> batches -> tokens -> .pt,
+    round-robin over ranks - driven here with the CPU oracle's SigLIP encode as the `vision_encode` callable."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import vlo_oracle as O
+    from videollm_online_b200.offline_encode import encode_directory, encoded_root
+    cfg, _, vs = tiny
+    R = cfg.frame_resolution
+    src = tmp_path / "clips_2fps_384"
+    src.mkdir()
+    rng = np.random.default_rng(0)
+    n_frames = {"a.avi": 5, "b.avi": 3, "c.avi": 4}
+    for name, n in n_frames.items():
+        w = cv2.VideoWriter(str(src / name), cv2.VideoWriter_fourcc(*"MJPG"), 2.0, (R, R))
+        if not w.isOpened():
+            pytest.skip("no MJPG encoder in this OpenCV build")
+        for _ in range(n):
+            w.write(rng.integers(0, 256, (R, R, 3), dtype=np.uint8))
+        w.release()
+    calls = []
+
+    def vision_encode(encoder, frames):
+        calls.append(int(frames.shape[0]))
+        return O.siglip_vision_encode(vs, cfg, frames)
+
+    kw = dict(src_root=str(src) + "/", vision_pretrained="google/siglip-large-patch16-384", vision_encode=vision_encode,
+              batch_size=2, embed_mark="2fps_384_1+3x3", save_bf16=True, world_size=2)
+    w0 = encode_directory(rank=0, **kw)
+    w1 = encode_directory(rank=1, **kw)
+    dst = encoded_root(str(src), "2fps_384_1+3x3", "google/siglip-large-patch16-384")
+    assert dst.endswith("clips_2fps_384_1+3x3_google--siglip-large-patch16-384")
+    assert [os.path.basename(p) for p in w0] == ["a.pt", "c.pt"] and [os.path.basename(p) for p in w1] == ["b.pt"]
+    assert calls == [2, 2, 1, 2, 2, 2, 1]                                  # batches of <= 2 frames per clip
+    for name, n in n_frames.items():
+        t = torch.load(os.path.join(dst, name.replace(".avi", ".pt")), weights_only=True)
+        assert t.dtype == torch.bfloat16 and tuple(t.shape) == (n, cfg.frame_num_tokens, cfg.vision_hidden_size)
+    # the saved tokens are the encoder's tokens of the decoded frames
+    from videollm_online_b200.video_ingest import read_video_resampled
+    fr = read_video_resampled(str(src / "b.avi"))
+    want = O.siglip_vision_encode(vs, cfg, fr).to(torch.bfloat16)
+    assert torch.equal(torch.load(os.path.join(dst, "b.pt"), weights_only=True), want)
