@@ -305,3 +305,28 @@ def test_offline_encode_directory_layout_and_sharding(tmp_path, tiny):
     fr = read_video_resampled(str(src / "b.avi"))
     want = O.siglip_vision_encode(vs, cfg, fr).to(torch.bfloat16)
     assert torch.equal(torch.load(os.path.join(dst, "b.pt"), weights_only=True), want)
+
+
+def test_committed_bench_records_carry_the_contract_keys():
+    """The bench lines measured on the B200 box this round (profiles/r01_bench_n*.json) have every key the driver's
+    contract names; guards bench.py's JSON against silently dropping one."""
+    import json
+    base = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"}
+    for n in (1, 4, 8):
+        d = json.loads((ROOT / "profiles" / f"r01_bench_n{n}.json").read_text().strip().splitlines()[-1])
+        assert base <= set(d), base - set(d)
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["higher_is_better"] is True and d["vs_baseline"] is None
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        assert d["e2e"]["h2d_bytes_per_step"] >= 3 * 384 * 384 and d["e2e"]["d2h_bytes_per_step"] == 32   # frame in, decision out
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+        assert d["gpu_launches"] > 0 and d["warmup"] >= 3
+        assert abs(d["value"] - n * d["steps"] / (d["ms_per_step"] * d["steps"] / 1e3)) < 1e-6 * d["value"]
+        if n == 1:
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
+    d1 = json.loads((ROOT / "profiles" / "r01_bench_n1.json").read_text().strip().splitlines()[-1])
+    d8 = json.loads((ROOT / "profiles" / "r01_bench_n8.json").read_text().strip().splitlines()[-1])
+    assert d8["value"] / d1["value"] >= 7.5            # north_star: >= 7.5x aggregate frames/s at 8 GPUs vs 1
