@@ -352,3 +352,32 @@ def test_full_width_layers_at_12k_context():
         assert _close(k, cache.k[layer][0, :, N:], 4e-2, 2e-2)[1] == 0.0
         assert _close(v, cache.v[layer][0, :, N:], 4e-2, 2e-2)[1] == 0.0
     eng.stream_close(kv.stream_id)
+
+
+def test_full_size_vit_tokens_and_visual_embed():
+    """BASELINE-size vision tower: SigLIP-L/16-384 (24 blocks, hidden 1024, 16 heads, 576 patches -> CLS + 3x3 pooled)
+    + the 1024 -> 4096 -> 4096 connector against the fp32 CPU oracle.  Batch 1 takes the small co-resident GEMM
+    configuration (64-token tiles), batch 3 the large-tile one; 576 tokens exercise the multi-block online softmax of
+    vit_attn_kernel (the tiny goldens have 36 tokens = one partial block).  An fp16-operand emulation of the oracle
+    deviates from the fp32 oracle by <= 2e-3 on these tokens (std 0.73), so VIT_ATOL leaves an order of magnitude."""
+    import vlo_oracle as O
+    from videollm_online_b200 import llama3_8b_siglip_l, weights as W
+    from videollm_online_b200.modeling_live import build_live
+    cfg = llama3_8b_siglip_l()
+    cfg.num_hidden_layers, cfg.vocab_size, cfg.intermediate_size = 1, 1024, 1024     # the decoder is not under test here
+    llm = W.synthetic_llm_state(cfg, seed=2)
+    vis = W.synthetic_vision_state(cfg, seed=1)
+    model, _ = build_live(config=cfg, llm_state=llm, vision_state=vis, set_vision_inside=True, device="cuda:0",
+                          max_streams=1, max_kv_tokens=256, max_step_tokens=32, max_vit_batch=4)
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (4, 3, cfg.frame_resolution, cfg.frame_resolution), dtype=torch.uint8, generator=g)
+    ref_tok = O.siglip_vision_encode(vis, cfg, frames)                     # fp32 [4, 10, 1024]
+    ref_emb = O.visual_embed(llm, vis, cfg, frames)                        # bf16 [40, 4096]
+    for sl in (slice(0, 1), slice(1, 4)):
+        emb, tok = model.engine.vit_encode(frames[sl].cuda(), return_vit_tokens=True)
+        assert tuple(tok.shape) == tuple(ref_tok[sl].shape)
+        mx, frac = _close(tok, ref_tok[sl], VIT_ATOL, 2e-2)
+        assert frac == 0.0, f"frames {sl}: vit tokens max err {mx}"
+        n = cfg.frame_num_tokens
+        mx, frac = _close(emb, ref_emb[sl.start * n: sl.stop * n], EMBED_ATOL, 3e-2)
+        assert frac == 0.0, f"frames {sl}: visual_embed max err {mx}"
