@@ -114,8 +114,6 @@ int lookup(vlo_engine* e, const std::string& name, int64_t expect_elems, const T
   return 0;
 }
 
-int swap_bn(int rows_b) { return rows_b <= 16 ? 16 : (rows_b <= 32 ? 32 : (rows_b <= 64 ? 64 : 128)); }
-
 // weights [n_out, k] x tokens [T, k] -> stream-K fp32 partial planes in e->part (persistent kernel)
 int gemm_partial(vlo_engine* e, const bf16* w, int n_out, const bf16* x, int T, int k, SkInfo* sk, cudaStream_t st) {
   int planes = 1;
