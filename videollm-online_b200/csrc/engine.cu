@@ -114,10 +114,30 @@ int lookup(vlo_engine* e, const std::string& name, int64_t expect_elems, const T
   return 0;
 }
 
+// SM partitioning experiment (default off = every persistent GEMM uses all SMs):
+//   VLO_DEC_CTAS=<n>  CTAs of the decoder / lm_head weight-streaming GEMMs (e.g. 132 with VLO_WS_STAGES=11)
+//   VLO_VIT_CTAS=<n>  CTAs of the ViT trunk GEMMs (e.g. 16), so both run side by side on disjoint SMs
+int dec_ctas() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLO_DEC_CTAS");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+int vit_ctas() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLO_VIT_CTAS");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 // weights [n_out, k] x tokens [T, k] -> stream-K fp32 partial planes in e->part (persistent kernel)
 int gemm_partial(vlo_engine* e, const bf16* w, int n_out, const bf16* x, int T, int k, SkInfo* sk, cudaStream_t st) {
   int planes = 1;
-  gemm_ws_plan(n_out, k, 0, 0, sk, &planes);
+  gemm_ws_plan(n_out, k, 0, dec_ctas(), sk, &planes);
   VLO_CHECK(static_cast<size_t>(planes) * T * n_out <= e->part_elems, "stream-K workspace too small");
   VLO_CHECK(planes <= kFixMaxPlanes, "stream-K produced more partial planes than the fix-up kernels unroll");
   GemmWsCall c{};
@@ -150,7 +170,7 @@ int gemm_ws_store16(int fmt, const void* w, int n_out, const void* x, int T, int
   c.ld_out = ld;
   c.bias = bias;
   c.act = act;
-  gemm_ws_plan(n_out, k, 1, 0, &c.sk, nullptr);
+  gemm_ws_plan(n_out, k, 1, fmt == FMT_BF16 ? dec_ctas() : 0, &c.sk, nullptr);
   return gemm_ws_launch(c, st);
 }
 
@@ -577,7 +597,7 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     g.bn = pick_bn(n_out, 1);
     g.weights_hot = 1;
     g.small_smem = small ? 1 : 0;
-    gemm_ws_plan(n_out, k, 1, 0, &g.sk, nullptr, (rows + g.bn - 1) / g.bn);
+    gemm_ws_plan(n_out, k, 1, vit_ctas(), &g.sk, nullptr, (rows + g.bn - 1) / g.bn);
     return gemm_ws_launch(g, st);
   };
   struct SkCall { SkInfo sk; int bn, xt; };
@@ -599,7 +619,7 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     int planes = 1;
     out->bn = g.bn;
     out->xt = (rows + g.bn - 1) / g.bn;
-    gemm_ws_plan(C, k, 0, 0, &g.sk, &planes, out->xt);
+    gemm_ws_plan(C, k, 0, vit_ctas(), &g.sk, &planes, out->xt);
     VLO_CHECK(planes <= 8 && static_cast<size_t>(planes) * rows * C <= e->v_part_elems, "ViT stream-K workspace too small");
     out->sk = g.sk;
     return gemm_ws_launch(g, st);
