@@ -330,3 +330,35 @@ def test_committed_bench_records_carry_the_contract_keys():
     d1 = json.loads((ROOT / "profiles" / "r01_bench_n1.json").read_text().strip().splitlines()[-1])
     d8 = json.loads((ROOT / "profiles" / "r01_bench_n8.json").read_text().strip().splitlines()[-1])
     assert d8["value"] / d1["value"] >= 7.5            # north_star: >= 7.5x aggregate frames/s at 8 GPUs vs 1
+
+
+def test_streamk_plan_through_the_c_abi_matches_its_definition():
+    """Stream-K decomposition of the persistent weight-streaming GEMM (csrc/streamk.h), queried through the C ABI's
+    planning call (d_out = NULL: no GPU work): units = (128-row tile, 64-wide k-block), CTA c owns
+    [floor(c*U/G), floor((c+1)*U/G)); a tile's partial planes = contributing CTAs.  The fix-up kernels unroll 8 planes."""
+    import bisect
+    import ctypes as C
+    from videollm_online_b200 import _lib
+    lib = _lib.load()
+
+    def planes_by_definition(rows_w, k, G, x_tiles=1):
+        tiles, kb = -(-rows_w // 128) * x_tiles, k // 64
+        U = tiles * kb
+        G = min(G, U)
+        lo = [(c * U) // G for c in range(G + 1)]
+        owner = lambda u: bisect.bisect_right(lo, u) - 1
+        return max(owner((t + 1) * kb - 1) - owner(t * kb) + 1 for t in range(tiles))
+
+    shapes = {"qkv": (6144, 4096), "o": (4096, 4096), "gate_up": (28672, 4096), "down": (4096, 14336),
+              "vit_out": (1024, 1024), "vit_fc2": (1024, 4096), "tiny": (256, 128), "one_tile": (128, 64)}
+    for name, (n, k) in shapes.items():
+        for G in (148, 132, 16, 3, 1):
+            for T in (11, 88):
+                got = C.c_int(-1)
+                rc = lib.vlo_op_gemm_ws(1, 0, None, n, None, T, k, None, n, T * n, None, 0, G, 0, C.byref(got), None)
+                assert rc == 0, lib.vlo_last_error()
+                bn = 16 if T <= 16 else 32 if T <= 32 else 64 if T <= 64 else 128
+                want = planes_by_definition(n, k, G, -(-T // bn))
+                assert got.value == want, (name, G, T, got.value, want)
+                if G == 148 and name in ("qkv", "o", "gate_up", "down"):
+                    assert got.value <= 8          # kFixMaxPlanes of the decoder fix-up kernels
