@@ -169,7 +169,8 @@ int vlo_op_gemm_ws(int fmt, int mode, const void* d_w, int rows_w, const void* d
  *   keys 0..kv_len-1 valid, the n_tok query tokens sit at positions kv_len-n_tok .. kv_len-1 (causal with
  *   offset, HF:masking_utils.py:263-272); d_out bf16 [n_tok, n_heads*head_dim]; d_ws fp32 scratch of
  *   vlo_op_attn_ws_bytes(). Replaces HF:models/llama/modeling_llama.py:272-285 (SDPA / flash-attn 2). */
-/* which generation of the KV-append attention kernel runs for this head layout: 2 = tcgen05 (csrc/attn_tc.cuh),
+/* which generation of the KV-append attention kernel runs for this head layout: 3 = tcgen05 with P in TMEM and a
+ * 192 KB K/V ring (csrc/attn_tc2.cuh, default), 2 = tcgen05 with P in shared memory (csrc/attn_tc.cuh, VLO_ATTN=2),
  * 1 = mma.sync (csrc/attn.cuh; forced by VLO_ATTN=1, or when n_heads/n_kv_heads does not divide 128) */
 int vlo_op_attn_version(int n_heads, int n_kv_heads);
 /* developer aid: with VLO_ATTN_TRACE=1 the tcgen05 attention kernel records clock64 stamps per CTA and role
@@ -178,6 +179,12 @@ int vlo_debug_attn_trace(long long* h_out, int n);
 int64_t vlo_op_attn_ws_bytes(int n_tok, int n_heads, int head_dim, int kv_len);
 int vlo_op_attn_kvappend(const void* d_q, const void* d_k, const void* d_v, void* d_out, float* d_ws, int n_tok,
                          int n_heads, int n_kv_heads, int head_dim, int kv_len, long long kv_stride, void* cuda_stream);
+/* Micro-loop of the same attention over n_layers separate K / V matrices (working set > L2), iters passes of back-to-back
+ * launches on one plan: what bench tools bracket with ONE CUDA-event pair (per-launch time incl. the PDL overlap of a real
+ * step).  skip_merge != 0 launches the main kernel only.  Mirrors vlo_bench_attn without an engine. */
+int vlo_op_attn_bench(const void* d_q, const void* d_k, const void* d_v, void* d_out, float* d_ws, int n_tok, int n_heads,
+                      int n_kv_heads, int head_dim, int kv_len, long long kv_stride, int n_layers,
+                      long long layer_stride_rows, int iters, int skip_merge, double* h_algo_bytes, void* cuda_stream);
 
 #ifdef __cplusplus
 }

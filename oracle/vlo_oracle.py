@@ -174,10 +174,43 @@ def _rotate_half(x):
     return torch.cat((-x2, x1), dim=-1)
 
 
-def llama_forward(sd: StateDict, cfg, inputs_embeds: torch.Tensor, cache: KVCache) -> torch.Tensor:
+class LoraAdapter:
+    """An UNMERGED PEFT LoRA adapter, as the reference runs it at inference (models/modeling_live.py:203-216:
+    PeftModel.from_pretrained(..., is_trainable=False), never merged).  peft is an un-vendored, un-pinned dependency
+    (README.md:54); its published Linear forward (peft/tuners/lora/layer.py, `Linear.forward`) is
+        result = base_layer(x);  result = result + lora_B(lora_A(dropout(x))) * scaling
+    with dropout the identity in eval mode and every op in the module dtype (bf16).  `state` uses the adapter's
+    own key names (base_model.model.<module>.lora_{A,B}[.<adapter>].weight)."""
+
+    def __init__(self, state: StateDict, scaling: float):
+        self.scaling = scaling
+        self.ab = {}
+        for k, a in state.items():
+            if ".lora_A" in k:
+                mod = k.split(".lora_A")[0]
+                mod = mod[len("base_model.model."):] if mod.startswith("base_model.model.") else mod
+                self.ab[mod] = (a, state[k.replace("lora_A", "lora_B")])
+
+    def linear(self, x: torch.Tensor, sd: StateDict, module: str) -> torch.Tensor:
+        y = F.linear(x, sd[module + ".weight"])
+        if module in self.ab:
+            a, b = self.ab[module]
+            y = y + F.linear(F.linear(x, a), b) * self.scaling
+        return y
+
+
+class _NoLora:
+    @staticmethod
+    def linear(x, sd, module):
+        return F.linear(x, sd[module + ".weight"])
+
+
+def llama_forward(sd: StateDict, cfg, inputs_embeds: torch.Tensor, cache: KVCache, lora: Optional[LoraAdapter] = None) -> torch.Tensor:
     """KV-append forward of LlamaForCausalLM with a DynamicCache and sdpa attention
     (HF:...llama.py:375-426 model, :303-333 layer, :251-289 attention, :146-168 RoPE, :182-184 MLP,
-    :485-487 lm_head on all positions).  inputs_embeds [q, H] (batch 1) -> logits [q, V]."""
+    :485-487 lm_head on all positions).  inputs_embeds [q, H] (batch 1) -> logits [q, V].
+    `lora`: optional unmerged adapter applied to every wrapped Linear (see LoraAdapter)."""
+    lin = (lora or _NoLora).linear
     h = inputs_embeds[None]
     q_len = h.shape[1]
     past = cache.get_seq_length()
@@ -192,9 +225,9 @@ def llama_forward(sd: StateDict, cfg, inputs_embeds: torch.Tensor, cache: KVCach
         p = f"model.layers.{i}."
         r = h
         x = rms_norm(h, sd[p + "input_layernorm.weight"], cfg.rms_norm_eps)
-        q = F.linear(x, sd[p + "self_attn.q_proj.weight"]).view(1, q_len, nh, hd).transpose(1, 2)
-        k = F.linear(x, sd[p + "self_attn.k_proj.weight"]).view(1, q_len, nkv, hd).transpose(1, 2)
-        v = F.linear(x, sd[p + "self_attn.v_proj.weight"]).view(1, q_len, nkv, hd).transpose(1, 2)
+        q = lin(x, sd, p + "self_attn.q_proj").view(1, q_len, nh, hd).transpose(1, 2)
+        k = lin(x, sd, p + "self_attn.k_proj").view(1, q_len, nkv, hd).transpose(1, 2)
+        v = lin(x, sd, p + "self_attn.v_proj").view(1, q_len, nkv, hd).transpose(1, 2)
         q = (q * cos) + (_rotate_half(q) * sin)
         k = (k * cos) + (_rotate_half(k) * sin)
         k_all, v_all = cache.update(i, k, v)
@@ -203,18 +236,31 @@ def llama_forward(sd: StateDict, cfg, inputs_embeds: torch.Tensor, cache: KVCach
         vr = v_all[:, :, None].expand(1, nkv, g, kv_len, hd).reshape(1, nh, kv_len, hd)
         a = F.scaled_dot_product_attention(q, kr, vr, attn_mask=mask[None, None], scale=hd ** -0.5)
         a = a.transpose(1, 2).reshape(1, q_len, nh * hd)
-        h = r + F.linear(a, sd[p + "self_attn.o_proj.weight"])
+        h = r + lin(a, sd, p + "self_attn.o_proj")
         r = h
         x = rms_norm(h, sd[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
-        x = F.linear(F.silu(F.linear(x, sd[p + "mlp.gate_proj.weight"])) * F.linear(x, sd[p + "mlp.up_proj.weight"]),
-                     sd[p + "mlp.down_proj.weight"])
+        x = lin(F.silu(lin(x, sd, p + "mlp.gate_proj")) * lin(x, sd, p + "mlp.up_proj"), sd, p + "mlp.down_proj")
         h = r + x
     h = rms_norm(h, sd["model.norm.weight"], cfg.rms_norm_eps)
-    return F.linear(h, sd["lm_head.weight"])[0]
+    return lin(h, sd, "lm_head")[0]
 
 
 def embed_tokens(sd: StateDict, ids: torch.Tensor) -> torch.Tensor:
     return F.embedding(ids, sd["model.embed_tokens.weight"])
+
+
+def joint_embed(sd: StateDict, vs: Optional[StateDict], cfg, input_ids: Optional[torch.Tensor], frames: Optional[torch.Tensor]) -> torch.Tensor:
+    """LiveMixin.joint_embed, models/modeling_live.py:29-42: embed `input_ids` (the <v> placeholder id lies one past
+    the embedding table: clamped, then overwritten) and scatter visual_embed(frames) into the <v> positions."""
+    if frames is None:
+        return embed_tokens(sd, input_ids)
+    if input_ids is None:
+        return visual_embed(sd, vs, cfg, frames)
+    emb = embed_tokens(sd, input_ids.clamp(max=cfg.vocab_size - 1)).clone()
+    v_mask = input_ids == cfg.v_placeholder_id
+    if v_mask.any():
+        emb[v_mask] = visual_embed(sd, vs, cfg, frames)
+    return emb
 
 
 def decide(last_logits: torch.Tensor, interval_id: int, threshold: float) -> int:

@@ -119,6 +119,69 @@ def golden_schedule(cfg):
     return {0: I, 1: I, 2: END, 5: E, 6: I, 7: END, 8: E, 9: I, 10: I, 11: I}
 
 
+def query_schedule(cfg):
+    """Second scripted run, WITH user queries (demo/cli.py:23-26): the narration request at t = 0.0 (rule 2 of
+    _call_for_streaming: answered right after the frame of that time) and a mid-stream query stamped 1.75 s that
+    arrives before the 2.0 s frame is consumed (rule 1: answered before the next frame).
+    call index -> forced id: frame0 (decision unused: the query pre-empts it) | response: 2 natural tokens, EOS |
+    frames .5, 1.0 silent, 1.5 speak | response: 1 natural, EOS | query response: 1 natural, EOS |
+    frames 2.0, 2.5 silent | 3.0 speak | response EOS | 3.5 silent."""
+    I, E, END = cfg.frame_token_interval_id, cfg.eos_token_id, cfg.stream_end_id
+    return {0: I, 3: E, 4: I, 5: I, 6: END, 8: E, 10: E, 11: I, 12: I, 13: END, 14: E, 15: I}
+
+
+QUERY_0 = 'Please narrate the video in real time.'      # demo/cli.py:23
+QUERY_MID = 'What is happening now?'
+QUERY_MID_AT, QUERY_MID_BEFORE_ITER = 1.75, 4           # stamped 1.75 s, submitted before iteration 4 (t = 2.0 s)
+
+
+class _HostIds(torch.Tensor):
+    """ids tensor whose .to('cuda') is a no-op, so the reference's query branch (demo/inference.py:42) runs
+    unmodified on a CPU host."""
+
+    def to(self, *a, **k):
+        return self
+
+
+class _CpuTok:
+    def __init__(self, tok):
+        self._tok = tok
+
+    def apply_chat_template(self, *a, **k):
+        return self._tok.apply_chat_template(*a, **k).as_subclass(_HostIds)
+
+    def decode(self, *a, **k):
+        return self._tok.decode(*a, **k)
+
+
+def run_reference_liveinfer(ref_inf, model, cfg, tok, schedule, video, queries_at_iter, n_iters=8):
+    """The reference's LiveInfer methods, unmodified, on CPU with scripted decisions.  queries_at_iter:
+    {iteration: [(query, video_time)]} submitted through input_query_stream before that iteration."""
+    import collections
+    li = ref_inf.LiveInfer.__new__(ref_inf.LiveInfer)
+    li.model, li.tokenizer = ScriptedModel(model, schedule), _CpuTok(tok)
+    li.hidden_size, li.frame_fps, li.frame_num_tokens = cfg.hidden_size, 2, cfg.frame_num_tokens
+    li.frame_token_interval_id, li.frame_token_interval_threshold = cfg.frame_token_interval_id, 0.725
+    li.eos_token_id = cfg.eos_token_id
+    li.inplace_output_ids = torch.zeros(1, 100, dtype=torch.long)
+    li._start_ids = tok.apply_chat_template([{'role': 'system', 'content': SYSTEM_PROMPT}], add_stream_prompt=True, return_tensors='pt')
+    li._added_stream_prompt_ids = tok.apply_chat_template([{}], add_stream_prompt=True, return_tensors='pt')
+    li._added_stream_generation_ids = tok.apply_chat_template([{}], add_stream_generation_prompt=True, return_tensors='pt')
+    li.query_queue, li.frame_embeds_queue = collections.deque(), collections.deque()
+    li.video_time, li.last_frame_idx = 0, -1
+    li.last_ids, li.past_key_values = torch.tensor([[]], dtype=torch.long), None
+    li.video_tensor = video
+    trace, notes = [], []
+    for i in range(n_iters):
+        for q, vt in queries_at_iter.get(i, []):
+            notes.append(li.input_query_stream(q, video_time=vt))
+        li.input_video_stream(i / li.frame_fps)
+        query, response = li()
+        kv = li.past_key_values.get_seq_length()
+        trace.append((i, query, response, int(li.last_ids.reshape(-1)[-1]), kv))
+    return trace, li.model.calls, notes
+
+
 @torch.no_grad()
 def main():
     torch.manual_seed(0)
@@ -165,30 +228,21 @@ def main():
 
     # ---- state machine: the reference's LiveInfer methods, unmodified, on CPU with scripted decisions
     tok = ByteTokenizer(cfg)
-    li = ref_inf.LiveInfer.__new__(ref_inf.LiveInfer)
-    li.model, li.tokenizer = ScriptedModel(model, golden_schedule(cfg)), tok
-    li.hidden_size, li.frame_fps, li.frame_num_tokens = cfg.hidden_size, 2, cfg.frame_num_tokens
-    li.frame_token_interval_id, li.frame_token_interval_threshold = cfg.frame_token_interval_id, 0.725
-    li.eos_token_id = cfg.eos_token_id
-    li.inplace_output_ids = torch.zeros(1, 100, dtype=torch.long)
-    li._start_ids = tok.apply_chat_template([{'role': 'system', 'content': SYSTEM_PROMPT}], add_stream_prompt=True, return_tensors='pt')
-    li._added_stream_prompt_ids = tok.apply_chat_template([{}], add_stream_prompt=True, return_tensors='pt')
-    li._added_stream_generation_ids = tok.apply_chat_template([{}], add_stream_generation_prompt=True, return_tensors='pt')
-    import collections
-    li.query_queue, li.frame_embeds_queue = collections.deque(), collections.deque()
-    li.video_time, li.last_frame_idx = 0, -1
-    li.last_ids, li.past_key_values = torch.tensor([[]], dtype=torch.long), None
     video = torch.randint(0, 256, (8, 3, S, S), dtype=torch.uint8, generator=g)
-    li.video_tensor = video
     fx["sm_video"] = video
-    trace = []
-    for i in range(8):
-        li.input_video_stream(i / li.frame_fps)
-        query, response = li()
-        kv = li.past_key_values.get_seq_length()
-        trace.append((i, query, response, int(li.last_ids.reshape(-1)[-1]), kv))
-    fx["sm_trace"] = trace
-    fx["sm_calls"] = li.model.calls
+    fx["sm_trace"], fx["sm_calls"], _ = run_reference_liveinfer(ref_inf, model, cfg, tok, golden_schedule(cfg), video, {})
+    # ---- same, with user queries (demo/cli.py:23 + a mid-stream query): rules 1 and 2 of _call_for_streaming and the
+    #      query branch of _call_for_response
+    fx["smq_trace"], fx["smq_calls"], fx["smq_notes"] = run_reference_liveinfer(
+        ref_inf, model, cfg, tok, query_schedule(cfg), video,
+        {0: [(QUERY_0, 0.0)], QUERY_MID_BEFORE_ITER: [(QUERY_MID, QUERY_MID_AT)]})
+
+    # ---- joint_embed (models/modeling_live.py:29-42): ids with <v> placeholders + frames
+    v_id = cfg.v_placeholder_id
+    jids = torch.tensor([[5, 7] + [v_id] * cfg.frame_num_tokens + [cfg.frame_token_interval_id] + [v_id] * cfg.frame_num_tokens + [9]])
+    fx["joint_ids"] = jids
+    fx["joint_embed"] = model.joint_embed(jids, frames[:2]).clone()
+    fx["joint_logits"] = model(input_ids=jids, frames=frames[:2], use_cache=False).logits[0].clone()
 
     torch.save(fx, OUT / "tiny_reference.pt")
     for k, v in fx.items():

@@ -86,3 +86,56 @@ def test_decide_rule():
     assert O.decide(x.clone(), 3, 0.725) == 5
     assert O.decide(x.clone(), 3, 0.5) == 3
     assert O.decide(x.clone(), 7, 0.725) == 3
+
+
+def _oracle_liveinfer(tiny, schedule):
+    cfg, llm, vis = tiny
+    from videollm_online_b200.config import SYSTEM_PROMPT
+    from videollm_online_b200.tokenization_live import ByteTokenizer
+    calls = [0]
+
+    def hook(logits, kind):
+        tok = schedule.get(calls[0])
+        calls[0] += 1
+        if tok is not None:
+            logits = logits.clone()
+            logits[tok] += 1000.0
+        return logits
+
+    return O.OracleLiveInfer(llm, vis, cfg, ByteTokenizer(cfg), frame_fps=2, system_prompt=SYSTEM_PROMPT, logit_hook=hook), calls
+
+
+def test_state_machine_with_queries_matches_reference_liveinfer(golden, tiny):
+    """The query path (demo/cli.py:23 narration request at t=0 + a mid-stream query): rules 1 and 2 of
+    _call_for_streaming (demo/inference.py:57-59, 72-74) and the user-query branch of _call_for_response (:42),
+    against the trace of the reference's own methods."""
+    cfg, llm, vis = tiny
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    import make_golden as MG
+    li, calls = _oracle_liveinfer(tiny, MG.query_schedule(cfg))
+    li.load_video(golden["sm_video"])
+    trace = []
+    for i in range(8):
+        if i == 0:
+            li.input_query_stream(MG.QUERY_0, video_time=0.0)
+        if i == MG.QUERY_MID_BEFORE_ITER:
+            li.input_query_stream(MG.QUERY_MID, video_time=MG.QUERY_MID_AT)
+        li.input_video_stream(i / 2)
+        query, response = li()
+        trace.append((i, query, response, int(li.last_ids.reshape(-1)[-1]), li.cache.get_seq_length()))
+    assert trace == golden["smq_trace"]
+    assert calls[0] == golden["smq_calls"]
+
+
+def test_joint_embed_matches_reference(golden, tiny):
+    """models/modeling_live.py:29-42 and forward(input_ids, frames) (models/live_llama/modeling_live_llama.py:24-67)."""
+    cfg, llm, vis = tiny
+    ids = golden["joint_ids"]
+    emb = O.joint_embed(llm, vis, cfg, ids[0], golden["frames"][:2])
+    ref = golden["joint_embed"][0]
+    assert emb.shape == ref.shape and emb.dtype == ref.dtype
+    is_v = ids[0] == cfg.v_placeholder_id
+    assert torch.equal(emb[~is_v], ref[~is_v])                       # token rows: exact gather
+    torch.testing.assert_close(emb[is_v].float(), ref[is_v].float(), rtol=2e-2, atol=2e-2)   # as test_visual_embed_matches_reference
+    logits = O.llama_forward(llm, cfg, ref, O.KVCache(cfg.num_hidden_layers))
+    assert torch.equal(logits, golden["joint_logits"])

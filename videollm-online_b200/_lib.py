@@ -79,6 +79,7 @@ SIGNATURES = {
     "vlo_debug_attn_trace": (_I, [C.POINTER(_LL), _I]),
     "vlo_op_attn_ws_bytes": (C.c_int64, [_I, _I, _I, _I]),
     "vlo_op_attn_kvappend": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _LL, _P]),
+    "vlo_op_attn_bench": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _LL, _I, _LL, _I, _I, C.POINTER(C.c_double), _P]),
 }
 
 _lock = threading.Lock()

@@ -1,0 +1,360 @@
+// KV-append attention, tcgen05 version 3 ("tc2"): same contract and partial (m, l, O) workspace as attn_tc.cuh,
+// re-laid-out so that a CTA keeps (almost) its whole share of the K/V stream in flight:
+//
+//   * P never touches shared memory.  The softmax threads write P_j as packed bf16 pairs straight into TMEM
+//     (tcgen05.st, lane = query row, 32-bit column = two consecutive keys) and O += P_j V_j is issued with the
+//     A operand IN TMEM (tcgen05.mma ... [d], [a], b-desc).  TMEM columns: S0 0..127 | S1 128..255 | O 256..383 |
+//     P0 384..447 | P1 448..511 — nothing aliases.
+//   * the 64 KB of shared memory this frees goes to the K/V ring: 192 KB = 3 stages of 128 keys (or 6 of 64),
+//     ALL of them requested before the grid dependency resolves (K/V rows of earlier steps do not depend on any
+//     kernel of this step), i.e. while the predecessor kernels (QKV fix-up, or the merge of the previous layer in
+//     the micro-loop) are still running.  For the single-stream 12k-token shape that is 192 of the ~335 KB a CTA
+//     consumes.
+//   * flat grid: one CTA per (item, kv head, split) entry of a host-built table, splits of an item are as even as
+//     the block count allows (blk0 = split * nblk / n_splits), and the host deals the splits so that the grid
+//     fills the SMs: 8 kv heads x 18 splits = 144 CTAs for one stream (was 16 x 8 = 128 with equal-size splits).
+//
+//   warp 0      TMA producer: Q tile, then the K and V tiles of every block (K and V have their own full/empty pairs)
+//   warp 1      MMA issuer:   S_j = Q K_j^T -> TMEM S[j&1];  O += P_j V_j with P_j read from TMEM
+//   warps 2-5   softmax:      tcgen05.ld S row -> online softmax (lazy O rescale) -> tcgen05.st P_j -> epilogue
+#pragma once
+#include <cuda.h>
+#include "attn_tc.cuh"
+
+namespace vlo {
+
+template <int BLK>
+struct Tc2Cfg {
+  static constexpr int kSub = BLK * 128;                         // [BLK keys x 64 dims] bf16, 128B-swizzled
+  static constexpr int kHalf = 2 * kSub;                         // one K or V tile
+  static constexpr int kStageBytes = 2 * kHalf;                  // K + V of one block
+  static constexpr int kStages = (192 * 1024) / kStageBytes;     // 3 (BLK = 128) / 6 (BLK = 64)
+  static constexpr int kQBytes = 2 * 128 * 128;                  // Q tile: 128 rows x 128 dims bf16
+  static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + 1024 + 512;
+};
+constexpr uint32_t kTc2ColS = 0, kTc2ColO = 256, kTc2ColP = 384;
+
+struct AttnTc2Params {
+  AttnParams base;
+  const int* cta_tab;     // [gridDim.x]: item << 16 | kv head << 8 | split
+  uint32_t v_lbo, v_sbo;  // V descriptor strides (bytes)
+  long long* dbg;         // optional timeline buffer (VLO_ATTN_TRACE)
+};
+
+// D[tmem] (+)= A[tmem] * B[smem desc]; A: lane = row, 32-bit column = two consecutive K elements (K-major)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// grid = (n_ctas); block = 192.
+template <int BLK>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                const __grid_constant__ CUtensorMap tm_q, const AttnTc2Params pp) {
+  using C = Tc2Cfg<BLK>;
+  constexpr int NS = C::kStages;
+  const AttnParams& p = pp.base;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* q_tile = smem;
+  uint8_t* kv_tile = smem + C::kQBytes;                     // NS stages: K tile | V tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_tile + NS * C::kStageBytes);
+  uint64_t* k_full = bars;                   // [NS]  TMA -> MMA (K tile landed)
+  uint64_t* k_empty = k_full + NS;           // [NS]  S_j done -> TMA
+  uint64_t* v_full = k_empty + NS;           // [NS]  TMA -> MMA (V tile landed)
+  uint64_t* v_empty = v_full + NS;           // [NS]  PV_j done -> TMA
+  uint64_t* s_full = v_empty + NS;           // [2]   S_j in TMEM
+  uint64_t* s_empty = s_full + 2;            // [2]   softmax has read S_j
+  uint64_t* p_full = s_empty + 2;            // [2]   P_j in TMEM (and O rescaled)
+  uint64_t* p_empty = p_full + 2;            // [2]   PV_j has consumed P buffer
+  uint64_t* o_done = p_empty + 2;            // [1]   PV_j complete (phase j)
+  uint64_t* q_ready = o_done + 1;            // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The CTA / item tables were uploaded by a memcpy at the start of the step (a full stream-order dependency of the
+  // step's first kernel), so they may be read before pdl_wait().
+  const int code = pp.cta_tab[blockIdx.x];
+  const int split = code & 255, kvh = (code >> 8) & 255;
+  const AttnItem it = p.items[code >> 16];
+  if (threadIdx.x == 0) VLO_TC_STAMP(0, 0);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_q);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_done, 1);
+    mbar_init(q_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // after the TMEM allocation (see gemm_ws.cuh)
+
+  const int G = p.n_heads / p.n_kv_heads;
+  const int kv_end = it.q_pos0 + it.q_count;
+  const int nblk_total = (kv_end + BLK - 1) / BLK;
+  const int blk0 = static_cast<int>((static_cast<long long>(split) * nblk_total) / it.n_splits);
+  const int nblk = static_cast<int>((static_cast<long long>(split + 1) * nblk_total) / it.n_splits) - blk0;
+  const uint32_t tS = tmem_base + kTc2ColS, tO = tmem_base + kTc2ColO, tP = tmem_base + kTc2ColP;
+  const int row_base = it.kv_row0 + kvh * it.kv_head_stride;
+
+  auto load_k = [&](int j) {
+    const int s = j % NS;
+    uint8_t* st = kv_tile + s * C::kStageBytes;
+    const int row = row_base + (blk0 + j) * BLK;
+    mbar_arrive_expect_tx(&k_full[s], C::kHalf);
+    tma_load_2d(st, &tm_k, &k_full[s], 0, row, kEvictFirst);
+    tma_load_2d(st + C::kSub, &tm_k, &k_full[s], 64, row, kEvictFirst);
+  };
+  auto load_v = [&](int j) {
+    const int s = j % NS;
+    uint8_t* st = kv_tile + s * C::kStageBytes + C::kHalf;
+    const int row = row_base + (blk0 + j) * BLK;
+    mbar_arrive_expect_tx(&v_full[s], C::kHalf);
+    tma_load_2d(st, &tm_v, &v_full[s], 0, row, kEvictFirst);
+    tma_load_2d(st + C::kSub, &tm_v, &v_full[s], 64, row, kEvictFirst);
+  };
+
+  // K/V rows of EARLIER steps do not depend on any kernel of this step: fill the whole ring with the blocks that end
+  // safely below this step's new tokens before waiting on the grid dependency.
+  int pre = 0;
+  if (warp == 0 && lane == 0) {
+    const int safe_end = it.q_pos0 - 128;  // a step appends at most 128 tokens per stream
+    for (; pre < nblk && pre < NS; ++pre) {
+      if ((blk0 + pre) * BLK + BLK - 1 >= safe_end) break;
+      load_k(pre);
+      load_v(pre);
+    }
+  }
+  if (threadIdx.x == 0) VLO_TC_STAMP(0, 1);
+  pdl_wait();
+  if (threadIdx.x == 0) VLO_TC_STAMP(0, 2);
+
+  if (nblk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // ------------------------------------------------------------ TMA producer
+        mbar_arrive_expect_tx(q_ready, C::kQBytes);
+        tma_load_3d(q_tile, &tm_q, q_ready, 0, kvh * G, it.q_tok0, kEvictNormal);
+        tma_load_3d(q_tile + kTcSub, &tm_q, q_ready, 64, kvh * G, it.q_tok0, kEvictNormal);
+        for (int j = pre; j < nblk; ++j) {
+          const int s = j % NS;
+          const uint32_t ph = (j / NS) & 1;
+          mbar_wait(&k_empty[s], ph ^ 1);
+          VLO_TC_STAMP(0, 4 + 2 * j);
+          load_k(j);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          VLO_TC_STAMP(0, 5 + 2 * j);
+          load_v(j);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, BLK, 0);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 1);
+        const uint32_t q_addr = smem_u32(q_tile);
+        mbar_wait(q_ready, 0);
+        tc_fence_after();
+        auto issue_pv = [&](int i) {
+          const int s = i % NS;
+          const int b = i & 1;
+          mbar_wait(&v_full[s], (i / NS) & 1);
+          mbar_wait(&p_full[b], (i >> 1) & 1);
+          tc_fence_after();
+          VLO_TC_STAMP(1, 3 * i + 2);
+          const uint32_t v_addr = smem_u32(kv_tile + s * C::kStageBytes + C::kHalf);
+#pragma unroll
+          for (int kk = 0; kk < BLK / 16; ++kk) {  // 16 keys per MMA: 8 packed TMEM columns of P
+            const uint64_t db = umma_desc_mn_sw128(v_addr + kk * 16 * 128, pp.v_lbo, pp.v_sbo);
+            umma_f16_ts(tO, tP + static_cast<uint32_t>(b * 64 + kk * 8), db, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&v_empty[s]);
+          umma_commit(&p_empty[b]);
+          umma_commit(o_done);
+        };
+        for (int j = 0; j < nblk; ++j) {
+          const int s = j % NS;
+          const int b = j & 1;
+          mbar_wait(&k_full[s], (j / NS) & 1);
+          VLO_TC_STAMP(1, 3 * j);
+          mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
+          tc_fence_after();
+          VLO_TC_STAMP(1, 3 * j + 1);
+          const uint32_t k_addr = smem_u32(kv_tile + s * C::kStageBytes);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {  // 16 dims per MMA
+            const uint64_t da = umma_desc_sw128(q_addr + (kk >> 2) * kTcSub + (kk & 3) * 32);
+            const uint64_t db = umma_desc_sw128(k_addr + (kk >> 2) * C::kSub + (kk & 3) * 32);
+            umma_f16(tS + b * 128, da, db, idesc_s, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&k_empty[s]);  // K tile is free as soon as QK^T has retired
+          umma_commit(&s_full[b]);
+          if (j >= 1) issue_pv(j - 1);
+        }
+        issue_pv(nblk - 1);
+      }
+    } else {
+      // -------------------------------------------------------------- softmax / correction / epilogue warps
+      const int q = warp & 3;
+      const int r = q * 32 + lane;       // TMEM lane == tile row == t * G + g
+      const int t = r / G;
+      const bool valid = r < it.q_count * G;
+      const bool warp_live = q * 32 < it.q_count * G;   // any query row in this warp's 32 lanes?
+      const int lim = valid ? it.q_pos0 + t : -1;       // last visible key (causal with offset)
+      const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+      const float c = p.scale_log2;
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nblk; ++j) {
+        const int b = j & 1;
+        mbar_wait(&s_full[b], (j >> 1) & 1);
+        tc_fence_after();
+        if (r == 0) VLO_TC_STAMP(2, 4 + 4 * j);
+        if (!warp_live) {  // no query row in these lanes: keep the barrier protocol going (their P / O rows stay
+                           // garbage; MMA rows are independent, they feed nothing but their own discarded O rows)
+          mbar_arrive(&s_empty[b]);
+          mbar_wait(&p_empty[b], ((j >> 1) & 1) ^ 1);
+          mbar_arrive(&p_full[b]);
+          continue;
+        }
+        const int key0 = (blk0 + j) * BLK;
+        const bool need_mask = key0 + BLK - 1 > it.q_pos0;  // block reaches past the first query's limit
+        float sv[BLK];
+#pragma unroll
+        for (int c0 = 0; c0 < BLK; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tS + lane_addr + b * 128 + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[c0 + i] = __uint_as_float(v[i]);
+        }
+        tc_fence_before();
+        mbar_arrive(&s_empty[b]);   // S[b] may be overwritten by block j+2
+        if (r == 0) VLO_TC_STAMP(2, 5 + 4 * j);
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < BLK; ++i)
+            if (key0 + i > lim) sv[i] = -INFINITY;
+        } else if (!valid) {
+#pragma unroll
+          for (int i = 0; i < BLK; ++i) sv[i] = -INFINITY;
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < BLK; i += 4) {
+          mx4[0] = fmaxf(mx4[0], sv[i]);
+          mx4[1] = fmaxf(mx4[1], sv[i + 1]);
+          mx4[2] = fmaxf(mx4[2], sv[i + 2]);
+          mx4[3] = fmaxf(mx4[3], sv[i + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // lazy rescale: keep the old reference max unless the new one is much larger
+        const float m_new = fmaxf(m_ref, mx);
+        const bool grow = (m_ref == -INFINITY) ? (m_new != -INFINITY) : ((m_new - m_ref) * c > kTcRescaleLog2);
+        const float m_use = grow ? m_new : m_ref;
+        const float alpha = (grow && m_ref != -INFINITY) ? exp2f((m_ref - m_new) * c) : 1.f;
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+          // O of this warp's 32 lanes must be rescaled: wait until PV_{j-1} has landed in TMEM
+          mbar_wait(o_done, (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_x32(tO + lane_addr + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_x32(tO + lane_addr + c0, v);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+        }
+        m_ref = m_use;
+        const float moff = (m_ref == -INFINITY) ? 0.f : m_ref * c;
+        // P = exp2(S c - m c) -> bf16 pairs -> TMEM; the P buffer must have been consumed by PV_{j-2} first
+        mbar_wait(&p_empty[b], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (r == 0) VLO_TC_STAMP(2, 6 + 4 * j);
+        float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float nmoff = -moff;
+#pragma unroll
+        for (int c0 = 0; c0 < BLK; c0 += 64) {
+          uint32_t w[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float p0 = ex2_approx(fmaf(sv[c0 + 2 * i], c, nmoff));
+            const float p1 = ex2_approx(fmaf(sv[c0 + 2 * i + 1], c, nmoff));
+            ps4[i & 3] += p0 + p1;
+            w[i] = pack_bf16(p0, p1);
+          }
+          tmem_st_x32(tP + lane_addr + static_cast<uint32_t>(b * 64 + c0 / 2), w);
+        }
+        l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[b]);
+        if (r == 0) VLO_TC_STAMP(2, 7 + 4 * j);
+      }
+      // ---- epilogue: partial (m, l, O) of this split; merged by attn_merge_kernel
+      mbar_wait(o_done, (nblk - 1) & 1);
+      tc_fence_after();
+      if (r == 0) VLO_TC_STAMP(2, 1);
+      const int rows = it.q_count * G;
+      const size_t slot = static_cast<size_t>(it.ws_slot0) + (static_cast<size_t>(kvh) * it.n_splits + split) * rows + r;
+      if (warp_live) {
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_x32(tO + lane_addr + c0, v0);
+          tmem_ld_x32(tO + lane_addr + c0 + 32, v1);
+          tmem_ld_wait();
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(p.ws_o + slot * kAttnHD + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dst[i] = make_float4(__uint_as_float(v0[4 * i]), __uint_as_float(v0[4 * i + 1]), __uint_as_float(v0[4 * i + 2]),
+                                   __uint_as_float(v0[4 * i + 3]));
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dst[8 + i] = make_float4(__uint_as_float(v1[4 * i]), __uint_as_float(v1[4 * i + 1]), __uint_as_float(v1[4 * i + 2]),
+                                       __uint_as_float(v1[4 * i + 3]));
+          }
+        }
+        if (valid) {
+          p.ws_ml[slot * 2] = m_ref;
+          p.ws_ml[slot * 2 + 1] = l_run;
+        }
+      }
+      if (r == 0) VLO_TC_STAMP(2, 2);
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace vlo

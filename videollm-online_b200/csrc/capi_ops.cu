@@ -126,4 +126,34 @@ int vlo_op_attn_kvappend(const void* d_q, const void* d_k, const void* d_v, void
   return 0;
 }
 
+/* Back-to-back launches of the KV-append attention over `n_layers` separate K / V matrices (layer l at
+ * d_k + l * layer_stride_rows * head_dim elements), `iters` passes: the micro-loop of vlo_bench_attn without an engine
+ * (bench tools time it with one CUDA-event pair).  The plan is built and uploaded once, as in a decoder step. */
+int vlo_op_attn_bench(const void* d_q, const void* d_k, const void* d_v, void* d_out, float* d_ws, int n_tok, int n_heads,
+                      int n_kv_heads, int head_dim, int kv_len, long long kv_stride, int n_layers,
+                      long long layer_stride_rows, int iters, int skip_merge, double* h_algo_bytes, void* cuda_stream) {
+  VLO_CHECK(n_layers > 0 && iters > 0 && layer_stride_rows >= static_cast<long long>(n_kv_heads) * kv_stride, "attn_bench: sizes");
+  AttnSeq s{};
+  s.q_tok0 = 0;
+  s.q_len = n_tok;
+  s.kv_len = kv_len;
+  s.kv_row0 = 0;
+  s.kv_head_stride = static_cast<int>(kv_stride);
+  static thread_local std::vector<uint8_t> stage;
+  stage.resize(attn_stage_bytes(n_tok, 1, n_heads, n_kv_heads));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  AttnPlan plan{};
+  if (attn_plan(&plan, d_ws, stage.data(), &s, 1, n_tok, n_heads, n_kv_heads, head_dim, st)) return -1;
+  VLO_CUDA(cudaStreamSynchronize(st));
+  plan.skip_merge = skip_merge;
+  if (h_algo_bytes) *h_algo_bytes = plan.algo_bytes;
+  const size_t lstride = static_cast<size_t>(layer_stride_rows) * head_dim * 2;
+  for (int it = 0; it < iters; ++it)
+    for (int l = 0; l < n_layers; ++l)
+      if (attn_run(plan, d_q, static_cast<const uint8_t*>(d_k) + l * lstride, static_cast<const uint8_t*>(d_v) + l * lstride,
+                   static_cast<long long>(n_kv_heads) * kv_stride, d_out, n_heads, n_kv_heads, head_dim, st))
+        return -1;
+  return 0;
+}
+
 }  // extern "C"

@@ -53,6 +53,9 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set it once per (device, kernel).
+int ensure_max_smem(const void* func, int bytes);
+
 // Launch counter (the bench reports how many of OUR kernels ran in the timed region).
 void count_launch(int n = 1);
 long long launch_count();
@@ -139,7 +142,10 @@ struct AttnPlan {
   void* d_items;
   int* d_tok_item;
   int n_items, max_splits, total_tokens;
-  int version;        // 1 = mma.sync kernel, 2 = tcgen05 kernel
+  int* d_cta_tab;     // v3: flat (item, kv head, split) table, one entry per CTA
+  int n_ctas;
+  int blk;            // keys per pipeline block
+  int version;        // 1 = mma.sync kernel, 2 = tcgen05 kernel (P in smem), 3 = tcgen05 kernel (P in TMEM, deep ring)
   int skip_merge;     // measurement only: launch the main kernel without the split-KV merge
   double algo_bytes;  // algorithmic HBM bytes of one attn_run over this plan (K+V rows read, Q read, out written)
 };

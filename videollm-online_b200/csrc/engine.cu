@@ -543,11 +543,7 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     g.bn = vit_bn(rows, C);
     if (gemm_launch(g, st)) return -1;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLO_CUDA(cudaFuncSetAttribute(vit_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kVitSmemBytes));
-    attr_set = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(vit_attn_kernel), kVitSmemBytes)) return -1;
   CUtensorMap tm_qkv;
   if (tmap_2d_sw128(e->v_qkv, rows, 3 * C, kVitBlk, FMT_F16, &tm_qkv)) return -1;
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // head_dim 64

@@ -92,12 +92,7 @@ template <int FMT, int BN, bool SWAP, int EPI>
 int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, dim3 grid,
                cudaStream_t stream) {
   auto kern = gemm_tn_kernel<FMT, BN, SWAP, EPI>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    VLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  GemmCfg<BN>::kSmemBytes));
-    attr_set = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), GemmCfg<BN>::kSmemBytes)) return -1;
   if (prof_on()) {
     const double esz = (EPI == EPI_STORE16) ? 2.0 : 4.0;
     const double bytes = 2.0 * args.k * (static_cast<double>(args.rows_a) + args.rows_b) +
@@ -245,16 +240,7 @@ int num_sms() {
 template <int FMT, int BN, int STAGES = ws_default_stages(BN)>
 int launch_ws(const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsArgs& a, cudaStream_t stream) {
   auto kern = gemm_ws_kernel<FMT, BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmWsCfg<BN, STAGES>::kSmemBytes));
-    if (getenv("VLO_DEBUG")) {
-      int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kGemmThreads, GemmWsCfg<BN, STAGES>::kSmemBytes);
-      fprintf(stderr, "vlo: gemm_ws<%d,%d> smem %d B -> %d CTA/SM\n", FMT, BN, GemmWsCfg<BN, STAGES>::kSmemBytes, nb);
-    }
-    attr_set = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), GemmWsCfg<BN, STAGES>::kSmemBytes)) return -1;
   if (prof_on()) {
     const double out_b = a.mode == 0 ? 4.0 * a.rows_x * a.rows_w : 2.0 * a.rows_x * a.rows_w;
     prof_begin(FMT == FMT_BF16 ? PROF_GEMM_STREAM : PROF_GEMM_VIT, stream,

@@ -27,6 +27,19 @@ bool pdl_enabled() {
   return on == 1 && !prof_on();
 }
 
+int ensure_max_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<int, const void*>> done;
+  int dev = 0;
+  VLO_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  for (const auto& d : done)
+    if (d.first == dev && d.second == func) return 0;
+  VLO_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.emplace_back(dev, func);
+  return 0;
+}
+
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches += n; }
 long long launch_count() { return g_launches.load(); }
