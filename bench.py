@@ -33,17 +33,29 @@ WORKLOAD = ("configs[1]: 1 stream/GPU, SigLIP-L/16-384 + Llama-3-8B, frame step 
             "(10-min video @2FPS position), synthetic 384x384 frames, seeded random weights")
 
 
+def static_config(world: int) -> dict:
+    """The `config` object of the JSON line: identical for the engine arm and the --impl reference arm (the driver
+    compares them); everything measured or run-dependent goes under "run"."""
+    return {"workload": WORKLOAD, "streams_per_gpu": 1, "kv_tokens_start": KV_START, "tokens_per_step": 11,
+            "vit_dtype": "fp16 operands / fp32 accumulate",
+            "parallelism": f"replicas x{world} (weights broadcast at init, no hot-path collective)",
+            "l2": "inputs larger than L2: every step streams 15.0 GB of weights + 1.6 GB of KV (L2 = 126 MB)",
+            "pipelining": "ViT+connector of the NEXT frames on a side CUDA stream during the decoder steps of the current ones "
+                          "(same work per frame; --encode-ahead frames per ViT pass, default 4)"}
+
+
 # ----------------------------------------------------------------------------- helpers
 def _ncu_traffic(kernel_key):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full summaries
-    (profiles/ncu_traffic.json, written by tools/profile_summary.py from the .ncu-rep files), or None."""
+    """(dram__bytes_read.sum + dram__bytes_write.sum per launch, commit of the capture) from the committed ncu --set full
+    summaries (profiles/ncu_traffic.json, written by tools/profile_summary.py from the .ncu-rep files), or (None, None)."""
     p = ROOT / "profiles" / "ncu_traffic.json"
     if not p.exists():
-        return None
+        return None, None
     try:
-        return json.loads(p.read_text()).get(kernel_key, {}).get("dram_bytes_per_launch")
+        d = json.loads(p.read_text())
+        return d.get(kernel_key, {}).get("dram_bytes_per_launch"), d.get(kernel_key, {}).get("commit", d.get("commit"))
     except Exception:
-        return None
+        return None, None
 
 
 def _peaks():
@@ -64,7 +76,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -115,7 +127,7 @@ def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 4, vit_laye
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
-    torch.set_num_threads(max(torch.get_num_threads(), max(1, avail // 2)))
+    torch.set_num_threads(max(1, avail // 2))   # pinned: one thread per physical core of the affinity mask
     sys.path.insert(0, str(ROOT / "oracle"))
     import vlo_bootstrap  # noqa: F401
     import vlo_oracle as O
@@ -181,7 +193,9 @@ def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 4, vit_laye
     # counted once at full size inside the sample and slightly over-weighted by the scaling -> conservative for us)
     vit_s = sum(tv) / len(tv) * (cfg.vision_num_hidden_layers / vit_layers)
     dec_s = sum(td) / len(td) * (cfg.num_hidden_layers / dec_layers)
+    per_step = [a * (cfg.vision_num_hidden_layers / vit_layers) + b * (cfg.num_hidden_layers / dec_layers) for a, b in zip(tv, td)]
     return vit_s + dec_s, {"vit_s_per_frame": vit_s, "decoder_s_per_step": dec_s, "threads": torch.get_num_threads(),
+                           "per_step_s": [round(x, 3) for x in per_step],
                            "sample": f"{n_steps} frame steps (+{n_warm} warm-up) of oracle/vlo_oracle.py: full-size SigLIP-L trunk truncated "
                                      f"to {vit_layers}/24 blocks and Llama-3-8B truncated to {dec_layers}/32 layers at kv={KV_START}, "
                                      "scaled to the full layer counts; fp32 ViT / bf16 decoder as the reference runs on a CPU host"}
@@ -198,10 +212,11 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "per-step working set (15 GB weights + 1.6 GB KV) >> cache"},
+            "config": static_config(int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": info["threads"], "kind": "port", "sample": info["sample"],
                              "vit_s_per_frame": info["vit_s_per_frame"], "decoder_s_per_step": info["decoder_s_per_step"],
-                             "host_cpus": os.cpu_count()},
+                             "host_cpus": os.cpu_count(), "per_step_s": info["per_step_s"],
+                             "note": "CPU port of the reference forward (oracle/), NOT the reference's GPU path: a reported baseline, not a speed-up claim"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     return line
@@ -231,14 +246,16 @@ def run_engine_arm(args):
     K, Wm = args.steps, max(3, args.warmup)
     n_frames = K + Wm + 8
     cap = ((KV_START + 11 * (2 * n_frames + 8) + 63) // 64) * 64 + 128
-    n_extra = 8 if (world == 1 and args.extras) else 1   # streams for the config-3 side measurement
-    eng = Engine(cfg, dev, max_streams=n_extra, max_kv_tokens=cap, max_step_tokens=128, max_vit_batch=n_extra)
+    if args.extras:
+        cap = max(cap, 13568)          # the literal configs[1] run ends at ~13.3k tokens
+    n_extra = 8 if args.extras else 1   # streams for the multi-stream side measurements
+    eng = Engine(cfg, dev, max_streams=n_extra, max_kv_tokens=cap, max_step_tokens=128, max_vit_batch=max(n_extra, args.encode_ahead))
 
     # ---- weights: rank 0 synthesises, everyone else receives them over NCCL/NVLink (init only)
     from videollm_online_b200.dist import broadcast_weights
     weights = W.synthetic_engine_weights(cfg, dev, cap, seed=0) if rank == 0 else None
     t_b0 = time.perf_counter()
-    weights = broadcast_weights(cfg, weights, dev, cap, dist)
+    weights = broadcast_weights(cfg, weights, dev, cap, dist, release_source=True)
     torch.cuda.synchronize()
     bcast_s = time.perf_counter() - t_b0
     eng.load_weights(weights)
@@ -275,48 +292,62 @@ def run_engine_arm(args):
     #      loaded clip LiveInfer prefetches the next frame the same way).  Every timed step still does one full
     #      ViT + one full decoder step; n frames in the region = n ViTs + n steps.
     side = torch.cuda.Stream(dev)
+    D = max(1, min(args.encode_ahead, eng.max_vit_batch))     # frames per encode-ahead ViT pass
     evs = [torch.cuda.Event(), torch.cuda.Event()]
     fes = [None, None]
-    fbufs = [torch.empty(1, 3, S, S, dtype=torch.uint8, device=dev) for _ in range(2)]
+    fbufs = [torch.empty(D, 3, S, S, dtype=torch.uint8, device=dev) for _ in range(2)]
 
-    def encode_on_side(i, slot, from_host, after=None):
+    def encode_on_side(i, slot, from_host, after=None, count=1):
+        """ViT + connector of frames [i, i+count) (indices modulo the synthetic clip) on the side stream"""
         if after is not None:
-            side.wait_event(after)      # frame i arrives while the step launched just before `after` is running
+            side.wait_event(after)      # the frames arrive while the step launched just before `after` is running
         else:
             side.wait_stream(stream)
+        idx = [(i + k) % n_frames for k in range(count)]
+        contiguous = idx[-1] - idx[0] == count - 1
         with torch.cuda.stream(side):
-            if from_host:   # e2e: this step's input comes from pinned host memory
-                fbufs[slot].copy_(frames_host[i:i + 1], non_blocking=True)
-                fes[slot] = model.visual_embed(fbufs[slot])
+            if from_host:   # e2e: these steps' inputs come from pinned host memory
+                for k, j in enumerate(idx):
+                    fbufs[slot][k:k + 1].copy_(frames_host[j:j + 1], non_blocking=True)
+                fes[slot] = model.visual_embed(fbufs[slot][:count])
             else:
-                fes[slot] = eng.vit_encode(frames_dev[i:i + 1])
+                fes[slot] = eng.vit_encode(frames_dev[idx[0]:idx[0] + count] if contiguous else frames_dev[idx])
             evs[slot].record(side)
 
     pre_evs = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def pipelined(n, base, from_host=False, read_back=False):
-        encode_on_side(base, 0, from_host)
+    def pipelined(n, base, from_host=False, read_back=False, step_fn=None):
+        """n frame steps; the ViT runs D frames at a time on the side stream, one group ahead of the decoder"""
+        n_groups = (n + D - 1) // D
+        encode_on_side(base, 0, from_host, count=min(D, n))
+        fe = None
         for i in range(n):
-            stream.wait_event(evs[i & 1])
-            fe = fes[i & 1]
-            fe.record_stream(stream)
-            packed[1:] = fe
-            pre_evs[i & 1].record(stream)
+            g, j = divmod(i, D)
+            if j == 0:
+                stream.wait_event(evs[g & 1])
+                fe = fes[g & 1]
+                fe.record_stream(stream)
+            if j == 0:
+                pre_evs[g & 1].record(stream)
             # the decoder step is enqueued FIRST: after a decision read-back the host is the critical path, and the
-            # ~100 launches of the next frame's ViT must not sit in front of the step's
-            eng.step([sid], [11], packed, row_ids=prefix, want_logits=True)
-            if i + 1 < n:
-                encode_on_side(base + i + 1, (i + 1) & 1, from_host, after=pre_evs[i & 1])
+            # launches of the next group's ViT must not sit in front of the step's
+            if step_fn is not None:
+                step_fn(i, fe[10 * j:10 * j + 10])
+            else:
+                packed[1:] = fe[10 * j:10 * j + 10]
+                eng.step([sid], [11], packed, row_ids=prefix, want_logits=True)
+            if j == 0 and g + 1 < n_groups:
+                encode_on_side(base + (g + 1) * D, (g + 1) & 1, from_host, after=pre_evs[g & 1], count=min(D, n - (g + 1) * D))
             if read_back:
                 eng.read_decisions(1)
 
     # ---- device-resident timing (value)
     eng.kv_fill_synthetic(sid, KV_START, seed=7 + rank)
-    pipelined(Wm, 0)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()       # 10 ms period, running from the warm-up on: the timed region alone can be 0.1 s
+    pipelined(Wm, 0)
+    barrier()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -338,6 +369,37 @@ def run_engine_arm(args):
     pipelined(K, Wm, from_host=True, read_back=True)
     torch.cuda.synchronize()
     e2e_s = reduce_max(time.perf_counter() - t0)
+    barrier()
+
+    # ---- the drop-in path: LiveInfer.input_video_stream + __call__ exactly as demo/cli.py:31-38 drives them (one frame per
+    #      iteration, decision read back, encode-ahead of the next frame), frames in PINNED HOST memory copied in per step.
+    #      Random weights never emit the protocol ids, so the documented test seam forces "silent" (the frame-step path;
+    #      speak / AR bursts are measured by the configs[4] extra).
+    from videollm_online_b200.config import LiveArguments, SYSTEM_PROMPT
+    from videollm_online_b200.inference import LiveInfer
+    from videollm_online_b200.tokenization_live import ByteTokenizer
+    from videollm_online_b200.modeling_live import StreamKV
+    eng.kv_truncate(sid, KV_START)
+    li = LiveInfer(LiveArguments(frame_fps=2, system_prompt=SYSTEM_PROMPT), model=model, tokenizer=ByteTokenizer(cfg),
+                   stream=StreamKV(eng, sid))
+    def _silent(dec, call):
+        dec.argmax_id = dec.argmax_prob_id = cfg.frame_token_interval_id
+        dec.p_interval = 1.0
+        return dec
+    li.decision_hook = _silent
+    li.load_video(frames_host[:Wm + K + 1], keep_on_host=True)
+    li.past_key_values = li._kv                      # resume at the 10-minute position (cache pre-filled above)
+    li.last_ids = torch.tensor([[cfg.frame_token_interval_id]])
+    for i in range(Wm):
+        li.input_video_stream(i / li.frame_fps)
+        li()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Wm, Wm + K):
+        li.input_video_stream(i / li.frame_fps)
+        li()
+    torch.cuda.synchronize()
+    e2e_li_s = reduce_max(time.perf_counter() - t0)
     barrier()
 
     # ---- strictly sequential variant (ViT, then decoder step, one stream) for reference
@@ -401,14 +463,14 @@ def run_engine_arm(args):
         gs, at = cls.get("gemm_weight_stream"), cls.get("attn_kvappend")
         roof = {"bound": "hbm", "kernel": "gemm_ws_kernel<bf16> (persistent stream-K weight streaming: 14.0 GB of the 16.6 GB/step)",
                 "achieved": micro_gemm["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": micro_gemm["achieved_gbs"] / hbm_peak,
-                "peak_source": which, "traffic": _ncu_traffic("gemm_ws_decoder"),
+                "peak_source": which, "traffic": _ncu_traffic("gemm_ws_decoder")[0], "traffic_commit": _ncu_traffic("gemm_ws_decoder")[1],
                 "avg_us_per_launch": micro_gemm["us_per_launch"], "algo_bytes_per_launch": micro_gemm["algo_bytes_per_launch"],
                 "method": "CUDA events around 4 back-to-back passes of the 128 decoder GEMM launches (q|k|v, o, gate|up, down of all 32 layers) on the engine's buffers, T=11",
                 "in_step_event_bracketed": {"achieved": gs["achieved_gbs"], "avg_us_per_launch": gs["avg_us_per_launch"],
                                             "note": "per-launch event pairs inside the step (PDL off): includes ~3-5 us bracket overhead per launch"}}
-        roof_attn = {"bound": "hbm", "kernel": "attn_tc_kernel + attn_merge_kernel (KV-append attention, tcgen05; one launch pair per layer)",
+        roof_attn = {"bound": "hbm", "kernel": "attn_tc2_kernel + attn_merge_kernel (KV-append attention, tcgen05 with P in TMEM, key-sliced softmax; one launch pair per layer)",
                      "achieved": micro_attn["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": micro_attn["achieved_gbs"] / hbm_peak,
-                     "peak_source": which, "traffic": _ncu_traffic("attn_tc"), "avg_us_per_launch": micro_attn["us_per_launch_incl_merge"],
+                     "peak_source": which, "traffic": _ncu_traffic("attn_tc2")[0], "traffic_commit": _ncu_traffic("attn_tc2")[1], "avg_us_per_launch": micro_attn["us_per_launch_incl_merge"],
                      "algo_bytes_per_launch": micro_attn["algo_bytes_per_launch"],
                      "method": "CUDA events around 4x32 back-to-back launch pairs over the 32 layers' caches (1.6 GB, > L2), q=11, kv=12011; merge kernel time included",
                      "main_kernel_only": {"achieved": micro_attn["achieved_gbs_main_only"], "frac": micro_attn["achieved_gbs_main_only"] / hbm_peak,
@@ -418,29 +480,80 @@ def run_engine_arm(args):
         roof_step = {"bound": "hbm", "algo_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_total / K / 1e3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (ms_total / K / 1e3) / 1e9 / hbm_peak}
 
-    # ---- side measurements (N=1 only; parity-test configs of BASELINE.json, reported as extras, not the headline)
+    # ---- side measurements: the other BASELINE.json configs, every rank runs them and the line carries the aggregate
+    #      (units summed over ranks / max time over ranks); reported as extras, not the headline
     extras = None
-    if world == 1 and args.extras:
+    if args.extras:
         extras = {}
+
+        def agg_sum(x):
+            if dist is None:
+                return x
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            return float(t.item())
+
+        def timed(fn):
+            """barrier, run fn() (enqueues work on `stream`, may sync), device time via CUDA events, max over ranks"""
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            a.record(stream)
+            fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - w0
+            return reduce_max(a.elapsed_time(b) / 1e3), reduce_max(wall)
+
         # (a) AR response tokens at 12k context: q = 1 steps, id fed back on the device side of the ABI
         eng.kv_truncate(sid, KV_START)
         one = torch.zeros(1, cfg.hidden_size, dtype=torch.bfloat16, device=dev)
         tid = torch.tensor([1234], dtype=torch.int64, device=dev)
         for _ in range(5):
             eng.step([sid], [1], one, row_ids=tid)
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
         n_ar = 64
-        for _ in range(n_ar):
-            eng.step([sid], [1], one, row_ids=tid)
-        a1.record(stream)
-        torch.cuda.synchronize()
-        extras["ar_decode"] = {"tokens_per_s": n_ar / (a0.elapsed_time(a1) / 1e3), "ms_per_token": a0.elapsed_time(a1) / n_ar,
-                               "kv_tokens": KV_START, "note": "greedy AR step (q=1) of one stream, device-timed, ids resident"}
-        # (b) configs[2]: 8 concurrent streams on one GPU (5-min clips -> kv ~6000), ViT batched over the streams,
+        def ar_loop():
+            for _ in range(n_ar):
+                eng.step([sid], [1], one, row_ids=tid)
+        t_dev, _ = timed(ar_loop)
+        extras["ar_decode"] = {"tokens_per_s": world * n_ar / t_dev, "ms_per_token": 1e3 * t_dev / n_ar, "kv_tokens": KV_START,
+                               "hbm_frac": (15009316864 + KV_START * 131072) / (t_dev / n_ar) / 1e9 / _peaks()[0],
+                               "note": "greedy AR step (q=1) of one stream per GPU, device-timed, ids resident"}
+
+        # (b) configs[1] literal: one stream from an EMPTY cache to 1200 frames (10 min @ 2 FPS) through real appends:
+        #     first frame = system prompt + frame, then 1199 steady frame steps; KV grows 0 -> ~13.2k
+        eng.stream_reset(sid)
+        n_lit = 1200 if not args.quick_extras else 120
+        start_ids = ByteTokenizer(cfg).apply_chat_template([{'role': 'system', 'content': SYSTEM_PROMPT}], add_stream_prompt=True)
+        first_rows = torch.tensor(list(start_ids) + [-1] * 10, dtype=torch.int64, device=dev)
+        first_packed = torch.zeros(len(start_ids) + 10, cfg.hidden_size, dtype=torch.bfloat16, device=dev)
+        marks = {}
+        def literal_step(i, fe):
+            if i == 0:
+                first_packed[len(start_ids):] = fe
+                eng.step([sid], [first_packed.shape[0]], first_packed, row_ids=first_rows, want_logits=True)
+            else:
+                packed[1:] = fe
+                eng.step([sid], [11], packed, row_ids=prefix, want_logits=True)
+            if i == n_lit - 101:
+                marks["ev"] = torch.cuda.Event(enable_timing=True)
+                marks["ev"].record(stream)
+                marks["kv"] = eng.kv_len(sid)
+
+        def literal_run():
+            pipelined(n_lit, 0, step_fn=literal_step)
+            marks["end"] = torch.cuda.Event(enable_timing=True)
+            marks["end"].record(stream)
+        t_dev, _ = timed(literal_run)
+        last100_s = reduce_max(marks["ev"].elapsed_time(marks["end"]) / 1e3)
+        extras["config1_literal"] = {"frames": n_lit, "frames_per_s_avg": world * n_lit / t_dev, "frames_per_s_last100": world * 100 / last100_s,
+                                     "kv_tokens_end": eng.kv_len(sid), "kv_tokens_at_last100_start": marks["kv"], "seconds": t_dev,
+                                     "note": "BASELINE configs[1] run literally: empty cache -> 1200 frames via real KV appends (pipelined ViT), device-timed"}
+
+        # (c) configs[2]: 8 concurrent streams on one GPU (5-min clips -> kv ~6000), ViT batched over the streams,
         #     one ragged decoder step of 8 x 11 tokens per tick
         S8 = n_extra
+        eng.stream_reset(sid)
         sids = [sid] + [eng.stream_open() for _ in range(S8 - 1)]
         for i, s_ in enumerate(sids):
             eng.kv_fill_synthetic(s_, 6000, seed=100 + i)
@@ -452,14 +565,8 @@ def run_engine_arm(args):
             eng.step(sids, [11] * S8, packed8, row_ids=rid8, want_logits=False)
         for i in range(3):
             tick8(i)
-        torch.cuda.synchronize()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_t = min(10, (n_frames - S8) // 1)
-        b0.record(stream)
-        for i in range(n_t):
-            tick8(i)
-        b1.record(stream)
-        torch.cuda.synchronize()
+        n_t = min(10, n_frames - S8)
+        t_dev, _ = timed(lambda: [tick8(i) for i in range(n_t)])
         ab8 = C.c_double(0)
         arr8 = (C.c_int32 * S8)(*sids)
         def attn8(it):
@@ -472,9 +579,84 @@ def run_engine_arm(args):
         extras["attn_kvappend_8streams"] = {"us_per_launch_incl_merge": ms8 * 1e3, "algo_bytes_per_launch": ab8.value,
                                             "achieved_gbs": ab8.value / 1e9 / (ms8 / 1e3), "frac_of_hbm_peak": ab8.value / 1e9 / (ms8 / 1e3) / hbm_peak8,
                                             "note": "same kernel, ragged batch of 8 streams x 11 query tokens at kv~6.1k each (configs[2] shape)"}
-        extras["multistream8"] = {"frames_per_s": S8 * n_t / (b0.elapsed_time(b1) / 1e3), "ms_per_tick": b0.elapsed_time(b1) / n_t,
-                                  "streams": S8, "kv_tokens_start": 6000,
+        extras["multistream8"] = {"frames_per_s": world * S8 * n_t / t_dev, "ms_per_tick": 1e3 * t_dev / n_t,
+                                  "streams": S8 * world, "kv_tokens_start": 6000,
                                   "note": "configs[2]: 8 concurrent streams/GPU, ViT batch 8 + one ragged 88-token decoder step per tick, device-timed"}
+
+        # (d) configs[4]: 8 streams/GPU (64 on 8 GPUs), mixed speak/silent with AR bursts up to 128 tokens, through the
+        #     multi-stream scheduler (one ragged step per tick carries frame steps, response prompts and AR tokens of
+        #     different streams).  Scripted protocol (random weights never emit it): stream s speaks at every 5th frame
+        #     (staggered by s), response lengths ~ seeded uniform{8..128}.
+        import random
+        from videollm_online_b200.multistream import StreamScheduler
+        for s_ in sids:
+            eng.stream_close(s_)
+        sch = StreamScheduler(model, ByteTokenizer(cfg), S8, frame_fps=2, system_prompt=SYSTEM_PROMPT, max_new_tokens=128)
+        rng = random.Random(1234 + rank)
+        lens = [[rng.randint(8, 128) for _ in range(64)] for _ in range(S8)]
+        n_resp, n_frames_seen = [0] * S8, [0] * S8
+        I_, E_, END_, A_ = cfg.frame_token_interval_id, cfg.eos_token_id, cfg.stream_end_id, 300
+        def mixed_hook(s_, d, n):
+            sess = sch.sessions[s_]
+            if sess._op[0] == "gen":
+                want = lens[s_][n_resp[s_] % 64]
+                tok = E_ if len(sess.resp) + 1 >= want else A_
+                if tok == E_:
+                    n_resp[s_] += 1
+            else:
+                k = n_frames_seen[s_]
+                n_frames_seen[s_] += 1
+                tok = END_ if (k > 0 and k % 5 == s_ % 5) else I_
+            d.argmax_id = d.argmax_prob_id = tok
+            d.p_interval = 1.0 if tok == I_ else 0.0
+            if tok != I_:
+                d.argmax_excl_id = tok
+            return d
+        sch.decision_hook = mixed_hook
+        clip = frames_dev[:min(n_frames, 32)]
+        for k, sess in enumerate(sch.sessions):
+            sess.load_video(torch.roll(clip, k, 0).repeat(4, 1, 1, 1))
+            eng.kv_fill_synthetic(sess.stream_id, 6000, seed=300 + k)
+            sess.started, sess.last_ids = True, [I_]
+        n_ticks = 24 if not args.quick_extras else 8
+        def mixed_run():
+            for i in range(n_ticks):
+                for sess in sch.sessions:
+                    sess.input_video_stream(i / 2)
+                while any(sess.pending_frames for sess in sch.sessions):   # bursts keep running across frame arrivals
+                    sch.tick()
+            sch.run_until_idle()
+        _, t_wall = timed(mixed_run)
+        toks = sum(len(ev[2]) for sess in sch.sessions for ev in sess.events if ev[0] == "response")
+        extras["config4_mixed"] = {"streams": S8 * world, "frames_per_s": agg_sum(sch.frames_done) / t_wall, "response_tokens_per_s": agg_sum(toks) / t_wall,
+                                   "responses": agg_sum(sum(n_resp)), "ticks": agg_sum(sch.ticks) / world, "seconds": t_wall, "max_new_tokens": 128,
+                                   "note": "configs[4]: 8 streams/GPU through StreamScheduler, scripted speak every 5th frame (staggered), response "
+                                           "lengths uniform{8..128}; wall time incl. the per-tick decision read-back (end to end)"}
+        for sess in sch.sessions:
+            eng.stream_close(sess.stream_id)
+
+        # (e) configs[3]: 1 stream/GPU at 10 FPS x 10 min = 66k-token cache (second engine on the SAME weight tensors, 8.7 GB of KV)
+        KV66 = 66000
+        w66 = dict(weights)
+        w66["rope.cos"], w66["rope.sin"] = W.rope_tables(cfg, KV66 + 512, dev)
+        eng66 = Engine(cfg, dev, max_streams=1, max_kv_tokens=KV66 + 512, max_step_tokens=128, max_vit_batch=1)
+        eng66.load_weights(w66)
+        s66 = eng66.stream_open()
+        eng66.kv_fill_synthetic(s66, KV66, seed=66 + rank)
+        def step66(i):
+            fe = eng.vit_encode(frames_dev[i:i + 1])
+            packed[1:] = fe
+            eng66.step([s66], [11], packed, row_ids=prefix, want_logits=True)
+        for i in range(3):
+            step66(i)
+        n66 = 10
+        t_dev, _ = timed(lambda: [step66(i) for i in range(n66)])
+        b66 = 15009316864 + (KV66 + 11 * 8) * 131072
+        extras["config3_66k"] = {"frames_per_s": world * n66 / t_dev, "ms_per_step": 1e3 * t_dev / n66, "kv_tokens": KV66,
+                                 "algo_bytes_per_step": b66, "hbm_frac": b66 / (t_dev / n66) / 1e9 / _peaks()[0],
+                                 "meets_10fps_per_stream": (n66 / t_dev) >= 10.0,
+                                 "note": "configs[3]: 1 stream/GPU at the 10 FPS x 10 min position (66k-token KV), sequential ViT + frame step, device-timed"}
+        eng66.close()
 
     if rank != 0:
         if dist is not None:
@@ -485,15 +667,16 @@ def run_engine_arm(args):
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "kv_tokens_start": KV_START, "kv_tokens_end": kv_end,
-                       "tokens_per_step": 11, "vit_dtype": "fp16 operands / fp32 accumulate", "parallelism": f"replicas x{world} (weights broadcast at init, no hot-path collective)",
-                       "l2": "inputs larger than L2: every step streams 15.0 GB of weights + 1.6 GB of KV (L2 = 126 MB)",
-                       "pipelining": "ViT+connector of frame i+1 on a side CUDA stream during decoder step i (same work per frame)",
-                       "sequential_ms_per_step": seq_ms, "sequential_frames_per_s": world * 1e3 / seq_ms,
-                       "weight_broadcast_s": bcast_s},
+            "config": static_config(world),
+            "run": {"kv_tokens_end": kv_end, "sequential_ms_per_step": seq_ms, "sequential_frames_per_s": world * 1e3 / seq_ms,
+                    "weight_broadcast_s": bcast_s},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(3 * S * S + 11 * 4 * 2 + 8), "d2h_bytes_per_step": 32,
-                    "ms_per_step": 1e3 * e2e_s / K, "api": "LiveLlamaForCausalLM.visual_embed + Engine.step (vlo_vit_encode / vlo_step_ids) + read_decisions"},
+                    "ms_per_step": 1e3 * e2e_s / K, "api": "LiveLlamaForCausalLM.visual_embed + Engine.step (vlo_vit_encode / vlo_step_ids) + read_decisions",
+                    "liveinfer": {"value": world * K / e2e_li_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_li_s / K,
+                                  "h2d_bytes_per_step": int(3 * S * S), "d2h_bytes_per_step": 32,
+                                  "api": "LiveInfer.input_video_stream + LiveInfer.__call__ per frame (demo/cli.py:31-38 loop), pinned-host clip, decision read back",
+                                  "vs_engine_api": (world * K / e2e_li_s) / e2e_fps}},
             "roofline": roof, "roofline_attn": roof_attn, "roofline_step": roof_step, "kernel_classes": cls}
     if extras:
         line["extras"] = extras
@@ -529,7 +712,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
-    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the AR-decode / 8-stream side measurements")
+    ap.add_argument("--encode-ahead", dest="encode_ahead", type=int, default=4,
+                    help="frames per encode-ahead ViT pass on the side stream (1 = one frame at a time)")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the side measurements of the other BASELINE configs")
+    ap.add_argument("--quick-extras", dest="quick_extras", action="store_true", help="shorter side measurements (dev runs)")
     args = ap.parse_args()
     with _StdoutToStderr() as guard:
         line = run_reference_arm(args) if args.impl == "reference" else run_engine_arm(args)

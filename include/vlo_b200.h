@@ -95,6 +95,10 @@ int vlo_stream_reset(vlo_engine* e, int stream_id);                 /* LiveInfer
 int vlo_stream_close(vlo_engine* e, int stream_id);
 int vlo_kv_len(vlo_engine* e, int stream_id, int* out_len);          /* Cache.get_seq_length() */
 int vlo_kv_truncate(vlo_engine* e, int stream_id, int new_len);      /* trim_past_key_values(0, new_len), models/modeling_live.py:170-171 */
+/* dst stream := the first n_tokens cache positions of src (device copy, all layers); dst's previous contents are dropped.
+ * The engine-side form of `trim_past_key_values(past_key_values, 0, n)` when the ORIGINAL cache must survive
+ * (stream_evaluate's look-ahead, models/modeling_live.py:112-113,170-171). */
+int vlo_kv_copy_prefix(vlo_engine* e, int src_stream_id, int dst_stream_id, int n_tokens, void* cuda_stream);
 /* test/bench hook: fill a stream's KV cache with deterministic pseudo-random values up to n_tokens
  * (pre-fill for the 12k-context measurements without replaying 1200 frames) */
 int vlo_kv_fill_synthetic(vlo_engine* e, int stream_id, int n_tokens, uint64_t seed, void* cuda_stream);

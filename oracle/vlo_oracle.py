@@ -205,7 +205,8 @@ class _NoLora:
         return F.linear(x, sd[module + ".weight"])
 
 
-def llama_forward(sd: StateDict, cfg, inputs_embeds: torch.Tensor, cache: KVCache, lora: Optional[LoraAdapter] = None) -> torch.Tensor:
+def llama_forward(sd: StateDict, cfg, inputs_embeds: torch.Tensor, cache: KVCache, lora: Optional[LoraAdapter] = None,
+                  return_hidden: bool = False) -> torch.Tensor:
     """KV-append forward of LlamaForCausalLM with a DynamicCache and sdpa attention
     (HF:...llama.py:375-426 model, :303-333 layer, :251-289 attention, :146-168 RoPE, :182-184 MLP,
     :485-487 lm_head on all positions).  inputs_embeds [q, H] (batch 1) -> logits [q, V].
@@ -242,6 +243,8 @@ def llama_forward(sd: StateDict, cfg, inputs_embeds: torch.Tensor, cache: KVCach
         x = lin(F.silu(lin(x, sd, p + "mlp.gate_proj")) * lin(x, sd, p + "mlp.up_proj"), sd, p + "mlp.down_proj")
         h = r + x
     h = rms_norm(h, sd["model.norm.weight"], cfg.rms_norm_eps)
+    if return_hidden:   # final-norm output [q, H] (test helper: crafting lm_head rows)
+        return h[0]
     return lin(h, sd, "lm_head")[0]
 
 
@@ -283,6 +286,96 @@ def fast_greedy_generate(sd: StateDict, cfg, inputs_embeds: torch.Tensor, cache:
             break
         inputs_embeds = embed_tokens(sd, torch.tensor([tok]))
     return out
+
+
+# =============================================================================== stream_evaluate
+def stream_evaluate(sd: StateDict, vs: Optional[StateDict], cfg, input_ids: torch.Tensor, labels: torch.Tensor,
+                    frames: torch.Tensor, ignore_token_id: int = -100, frame_token_interval_threshold: float = 0.0) -> torch.Tensor:
+    """LiveMixin.stream_evaluate, models/modeling_live.py:44-168, batch 1: one teacher-forced forward over the whole
+    conversation (all-position logits), then per turn LM perplexity / time difference / fluency / LM correctness; a turn
+    whose frames are all predicted "silent" continues the stream on a cache trimmed to the turn's last frame token
+    (:112-141; `trim_past_key_values(pkv, 0, stop)` == keep the first `stop` positions).
+    Returns tensor [lm_ppl, frame_diff, fluency, lm_correctness]."""
+    assert input_ids.size(0) == labels.size(0) == 1
+    input_id, label = input_ids[0], labels[0]
+    zero, one = torch.tensor(0, dtype=torch.int), torch.tensor(1, dtype=torch.int)
+    turn_stops = ((input_id == cfg.eos_token_id).nonzero() + 1)[:, 0].tolist()
+    turn_starts = [0] + turn_stops[:-1]
+    num_turns = len(turn_starts)
+    cache = KVCache(cfg.num_hidden_layers)
+    logit = llama_forward(sd, cfg, joint_embed(sd, vs, cfg, input_id, frames), cache)
+    v_id = cfg.v_placeholder_id
+    use_interval = cfg.frame_token_interval_id is not None
+    interval_id = cfg.frame_token_interval_id if use_interval else cfg.eos_token_id
+    fnt = int(cfg.frame_token_cls) + (cfg.frame_token_pooled[0] * cfg.frame_token_pooled[1] if cfg.frame_token_pooled else 0)
+    past_num_frames = 0
+    lm_ppls, frame_diffs, fluencies, lm_correctness = [], [], [], []
+    for r, (turn_start, turn_stop) in enumerate(zip(turn_starts, turn_stops)):
+        turn_label = label[turn_start:turn_stop]
+        turn_learn_mask = turn_label != ignore_token_id
+        if not turn_learn_mask.any():
+            continue
+        turn_logit = logit[turn_start:turn_stop]
+        turn_input_id = input_id[turn_start:turn_stop]
+        turn_v_mask = turn_input_id == v_id
+        turn_num_frames = turn_v_mask.sum() // fnt
+        turn_stream_mask = turn_v_mask & turn_learn_mask
+        turn_lm_mask = turn_learn_mask & ~turn_stream_mask
+        if turn_lm_mask.any():                                                            # :86-96
+            ml, mt = turn_logit[turn_lm_mask], turn_label[turn_lm_mask]
+            lm_ppls.append(F.cross_entropy(ml, mt).exp())
+            wrong = ml.argmax(dim=-1) != mt
+            num_lm_correct_tokens = wrong.nonzero()[0, 0] if wrong.any() else (~wrong).sum()
+            lm_correctness.append(num_lm_correct_tokens / mt.numel())
+        if turn_stream_mask.any():                                                        # :99-142
+            score = turn_logit.softmax(dim=-1)[turn_stream_mask]
+            if frame_token_interval_threshold > 0:
+                score[score[:, interval_id] < frame_token_interval_threshold] = 0
+            pred = score.argmax(dim=-1) != interval_id
+            if pred.any():
+                frame_diff = turn_stream_mask.sum() - pred.nonzero()[0, 0] - 1
+            else:
+                last_stream_idx = turn_stream_mask.nonzero()[-1, 0]
+                if r == num_turns - 1:
+                    frame_diff = zero
+                else:
+                    next_nf = (input_id[turn_starts[r + 1]:turn_stops[r + 1]] == v_id).sum() // fnt
+                    n_app = min(next_nf, turn_num_frames - 1)
+                    if n_app == 0:
+                        frame_diff = zero
+                    else:
+                        app_frames = frames[past_num_frames + turn_num_frames: past_num_frames + turn_num_frames + n_app]
+                        ph = ([interval_id] if use_interval else []) + [v_id] * fnt
+                        app_ids = torch.tensor(ph * int(n_app), dtype=torch.long)
+                        trimmed = KVCache(cfg.num_hidden_layers)
+                        stop = int(turn_start + last_stream_idx + 1)
+                        for li in range(cfg.num_hidden_layers):
+                            trimmed.k[li], trimmed.v[li] = cache.k[li][..., :stop, :], cache.v[li][..., :stop, :]
+                        app_logit = llama_forward(sd, cfg, joint_embed(sd, vs, cfg, app_ids, app_frames), trimmed)
+                        idxs = torch.arange(len(ph) - 1, len(app_ids), len(ph))
+                        app_score = app_logit[idxs].softmax(dim=-1)
+                        if frame_token_interval_threshold > 0:
+                            app_score[app_score[:, interval_id] < frame_token_interval_threshold] = 0
+                        app_pred = app_score.argmax(dim=-1) != interval_id
+                        frame_diff = -(app_pred.nonzero()[0, 0] + 1) if app_pred.any() else -n_app
+            frame_diffs.append(torch.as_tensor(frame_diff).abs())
+        if turn_lm_mask.any() and turn_stream_mask.any():                                 # :145-154
+            n_v = turn_stream_mask.sum()
+            n_valid = mt.numel() + n_v
+            if frame_diff == 0:
+                fluency = (n_v + num_lm_correct_tokens) / n_valid
+            elif frame_diff > 0:
+                fluency = (n_v - frame_diff) / n_valid
+            else:
+                fluency = (n_v - 1) / n_valid
+            fluencies.append(fluency)
+        past_num_frames += turn_num_frames
+    lm_ppl = torch.stack(lm_ppls).mean() if lm_ppls else one
+    frame_diff = torch.stack(frame_diffs).float().mean() if frame_diffs else zero
+    fluency = torch.stack([torch.as_tensor(f) for f in fluencies]).float().mean() if fluencies else one
+    lm_c = torch.stack([torch.as_tensor(c) for c in lm_correctness]).float().mean() if lm_correctness else one
+    return torch.stack([torch.as_tensor(lm_ppl).float(), torch.as_tensor(frame_diff).float(), torch.as_tensor(fluency).float(),
+                        torch.as_tensor(lm_c).float()])
 
 
 # =============================================================================== state machine

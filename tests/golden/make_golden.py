@@ -182,6 +182,46 @@ def run_reference_liveinfer(ref_inf, model, cfg, tok, schedule, video, queries_a
     return trace, li.model.calls, notes
 
 
+def stream_eval_sample(cfg, tok):
+    """A two-turn conversation for stream_evaluate (models/modeling_live.py:44-168): system prompt, 3 frames, an
+    assistant reply, 2 frames, an assistant reply.  Labels follow data/stream.py's convention: the LAST <v> of a frame
+    predicts "," (keep watching) or "]\n" (speak); assistant text is teacher-forced; everything else is ignored."""
+    msgs = [{'role': 'system', 'content': 'sys'}, {'role': 'stream', 'num_frames': 3}, {'role': 'assistant', 'content': 'ab'},
+            {'role': 'stream', 'num_frames': 2}, {'role': 'assistant', 'content': 'c'}]
+    ids = tok.apply_chat_template(msgs, return_tensors='pt')
+    input_id = ids[0]
+    label = torch.full_like(input_id, -100)
+    n, fnt, v_id = input_id.numel(), cfg.frame_num_tokens, cfg.v_placeholder_id
+    i = 0
+    while i < n:
+        if input_id[i] == v_id and (i + 1 == n or input_id[i + 1] != v_id):       # last <v> of a frame
+            label[i] = input_id[i + 1]
+        i += 1
+    # assistant spans: tokens after "Assistant:" up to and including EOS are learned (shifted by one)
+    txt_colon = tok.encode(':')[0]
+    eos = cfg.eos_token_id
+    for e in (input_id == eos).nonzero()[:, 0].tolist():
+        st = e
+        while input_id[st] != txt_colon:
+            st -= 1
+        for j in range(st, e):
+            label[j] = input_id[j + 1]
+    return ids, label[None]
+
+
+def craft_silent_lm_head(llm_state, cfg, hidden, positions):
+    """Random weights never predict the interval token, so stream_evaluate's "reply after the turn" branch (:110-141)
+    would stay dark.  Give the interval id an lm_head row aligned with the final hidden states at `positions`
+    (|h_p|^2 dominates the cross terms), which makes exactly those frames read as "keep watching"."""
+    row = hidden[positions].float().sum(0)
+    row = row / row.norm() * 40.0
+    sd = dict(llm_state)
+    w = sd["lm_head.weight"].clone()
+    w[cfg.frame_token_interval_id] = row.to(w.dtype)
+    sd["lm_head.weight"] = w
+    return sd, w[cfg.frame_token_interval_id].clone()
+
+
 @torch.no_grad()
 def main():
     torch.manual_seed(0)
@@ -243,6 +283,25 @@ def main():
     fx["joint_ids"] = jids
     fx["joint_embed"] = model.joint_embed(jids, frames[:2]).clone()
     fx["joint_logits"] = model(input_ids=jids, frames=frames[:2], use_cache=False).logits[0].clone()
+
+    # ---- stream_evaluate (models/modeling_live.py:44-168): the reference's own method on a two-turn sample.
+    #      trim_past_key_values (:170-171) assumes the legacy tuple cache and breaks on transformers 5.5's DynamicCache
+    #      (SURVEY 8c); it is replaced by its meaning: a copy of the cache cropped to the first `stop` positions.
+    import copy
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import vlo_oracle as O
+    se_ids, se_labels = stream_eval_sample(cfg, tok)
+    se_frames = torch.randint(0, 256, (5, 3, S, S), dtype=torch.uint8, generator=g)
+    hid = O.llama_forward(llm_state, cfg, O.joint_embed(llm_state, vision_state, cfg, se_ids[0], se_frames),
+                          O.KVCache(cfg.num_hidden_layers), return_hidden=True)
+    v_last = [i for i in range(se_ids.shape[1]) if se_labels[0, i] != -100 and se_ids[0, i] == cfg.v_placeholder_id]
+    se_state, se_row = craft_silent_lm_head(llm_state, cfg, hid, v_last[:3])      # the three frames of turn 1 stay silent
+    model.lm_head.weight.data[cfg.frame_token_interval_id] = se_row
+    type(model).trim_past_key_values = lambda self, pkv, start, stop: (lambda c: (c.crop(stop), c)[1])(copy.deepcopy(pkv))
+    fx["se_ids"], fx["se_labels"], fx["se_frames"], fx["se_lm_head_row"] = se_ids, se_labels, se_frames, se_row
+    for thr in (0.0, 0.9):
+        fx[f"se_metrics_thr{thr}"] = model.stream_evaluate(se_ids, se_labels, se_frames, frame_token_interval_threshold=thr).clone()
+    model.lm_head.weight.data[cfg.frame_token_interval_id] = llm_state["lm_head.weight"][cfg.frame_token_interval_id]
 
     torch.save(fx, OUT / "tiny_reference.pt")
     for k, v in fx.items():

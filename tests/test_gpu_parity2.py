@@ -397,3 +397,107 @@ def test_attention_at_66k_keys_vs_sdpa():
         err = float((out.float() - ref).abs().max())
         _report("attn_66k_keys", n_tok=n_tok, max_err=err)
         assert err < 2e-2 and bool(torch.isfinite(out.float()).all()), err
+
+
+# ------------------------------------------------------------------------------------------- stream_evaluate
+def test_stream_evaluate_vs_reference(golden, tiny):
+    """stream_evaluate on the engine's cache (teacher-forced chunks through vlo_step_ids +
+    vlo_last_step_logits, look-ahead on a vlo_kv_copy_prefix scratch stream) against the reference's own method.
+    Integer-valued metrics (frame_diff, fluency, lm_correctness) must agree exactly; perplexity is exp(mean CE) of
+    random weights (~e^50), compared in log space within the logit tolerance."""
+    from videollm_online_b200.modeling_live import build_live
+    cfg, llm, vis = tiny
+    sd = dict(llm)
+    w = sd["lm_head.weight"].clone()
+    w[cfg.frame_token_interval_id] = golden["se_lm_head_row"]
+    sd["lm_head.weight"] = w
+    model, _ = build_live(config=cfg, llm_state=sd, vision_state=vis, set_vision_inside=True, device="cuda:0",
+                          max_streams=2, max_kv_tokens=256, max_step_tokens=32, max_vit_batch=4)   # 91 tokens -> 3 chunks
+    for thr in (0.0, 0.9):
+        got = model.stream_evaluate(golden["se_ids"].cuda(), golden["se_labels"].cuda(), golden["se_frames"].cuda(),
+                                    frame_token_interval_threshold=thr).cpu()
+        ref = golden[f"se_metrics_thr{thr}"].float()
+        _report("stream_evaluate", thr=thr, log_ppl=float(got[0].log()), log_ppl_ref=float(ref[0].log()),
+                frame_diff=float(got[1]), fluency=float(got[2]), lm_correctness=float(got[3]))
+        assert torch.equal(got[1:], ref[1:]), (got, ref)
+        assert abs(float(got[0].log()) - float(ref[0].log())) < LOGIT_ATOL, (got, ref)
+    # pre-extracted features instead of raw frames (the evaluation path of the reference: data/stream.py:90-91)
+    feats = golden["vit_tokens"]          # [4, 10, C] of golden["frames"]; just exercise the connector-only route
+    assert model.visual_embed(feats.cuda()).shape[0] == 4 * cfg.frame_num_tokens
+
+
+# ------------------------------------------------------------------------------------------- f2 / f3 on the GPU
+def _write_clip(cv2, np, path, n, size, fps, seed):
+    w = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"MJPG"), fps, size)
+    if not w.isOpened():
+        pytest.skip("no MJPG encoder in this OpenCV build")
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        f = rng.integers(0, 256, (size[1], size[0], 3), dtype=np.uint8)
+        f[:, : size[0] // 2] = (i * 9) % 256          # large flat areas survive the JPEG round trip
+        w.write(f)
+    w.release()
+
+
+def test_cli_on_a_video_file(built, tiny, tmp_path):
+    """demo/cli.py's flow on a clip ON DISK (decode -> 2 FPS resample -> letterbox, data/utils.py:51-66 +
+    demo/inference.py:111-115) feeding the engine: `cli.main(LiveInfer, video=<path>)`.  The frame embeddings the
+    state machine consumed must equal the oracle's on the frames the ingest produced."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    import vlo_oracle as O
+    from videollm_online_b200 import cli
+    from videollm_online_b200.config import LiveArguments, SYSTEM_PROMPT
+    from videollm_online_b200.inference import LiveInfer
+    from videollm_online_b200.video_ingest import read_video_resampled
+    cfg, llm, vis = tiny
+    model, tok = built
+    path = tmp_path / "clip.avi"
+    _write_clip(cv2, np, path, 90, (160, 90), 30.0, seed=3)          # 3 s of 16:9 video at 30 fps -> 6 frames at 2 FPS
+    li = LiveInfer(LiveArguments(frame_fps=2, system_prompt=SYSTEM_PROMPT), model=model, tokenizer=tok)
+    I, E = cfg.frame_token_interval_id, cfg.eos_token_id
+    sched = {0: I, 1: E}                                             # narration query answered with an immediate EOS
+    li.decision_hook = lambda dec, call: _force(cfg, dec, sched.get(call, I))
+    fps, history = cli.main(li, video=str(path), n_iters=6, quiet=True)
+    assert li.num_video_frames == 6 and tuple(li.video_tensor.shape) == (6, 3, cfg.frame_resolution, cfg.frame_resolution)
+    assert fps > 0 and len(history["conversation"]) == 7             # query + response at t=0, then 5 silent frames
+    assert history["conversation"][0]["role"] == "user" and history["conversation"][1]["role"] == "assistant"
+    frames = read_video_resampled(str(path), fps=2, resolution=cfg.frame_resolution)
+    assert torch.equal(frames, li.video_tensor.cpu())
+    assert int(frames[:, :, :20].max()) == 0                         # letterbox bars of the 16:9 source
+    ref = O.visual_embed(llm, vis, cfg, frames)
+    got = model.visual_embed(li.video_tensor)
+    assert _close(got, ref, EMBED_ATOL, 3e-2)[1] == 0.0
+    # KV accounting: start prompt + 11 + query prompt + 1 (EOS) + 5 x (stream prompt / interval + 10)
+    assert li.past_key_values.get_seq_length() > 6 * 11
+    model.engine.stream_close(li._kv.stream_id)
+
+
+def test_offline_encode_directory_on_the_engine(built, tiny, tmp_path):
+    """distributed_encode's host loop (data/utils.py:86-104) with `build_live_vision(config, engine)` as
+    the encoder: batches larger than the engine's max_vit_batch are chunked, the saved bf16 features equal the oracle's
+    SigLIP tokens (models/vision_live.py:10-30) of the decoded frames."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    import vlo_oracle as O
+    from videollm_online_b200.offline_encode import encode_directory, encoded_root
+    from videollm_online_b200.vision_live import build_live_vision
+    from videollm_online_b200.video_ingest import read_video_resampled
+    cfg, _, vis = tiny
+    model, _ = built
+    R = cfg.frame_resolution
+    src = tmp_path / "clips_2fps_384"
+    src.mkdir()
+    for k, (name, n) in enumerate({"a.avi": 11, "b.avi": 3}.items()):
+        _write_clip(cv2, np, src / name, n, (R, R), 2.0, seed=10 + k)
+    enc, fn = build_live_vision(cfg, model.engine)
+    written = encode_directory(src_root=str(src) + "/", vision_pretrained="google/siglip-large-patch16-384", vision_encode=fn,
+                               encoder=enc, batch_size=256, embed_mark="2fps_384_1+3x3", save_bf16=True, device="cuda:0")
+    assert [pathlib.Path(p).name for p in written] == ["a.pt", "b.pt"]
+    dst = encoded_root(str(src), "2fps_384_1+3x3", "google/siglip-large-patch16-384")
+    for name, n in (("a", 11), ("b", 3)):
+        feats = torch.load(pathlib.Path(dst) / f"{name}.pt")
+        assert feats.dtype == torch.bfloat16 and tuple(feats.shape) == (n, cfg.frame_num_tokens, cfg.vision_hidden_size)
+        ref = O.siglip_vision_encode(vis, cfg, read_video_resampled(str(src / f"{name}.avi")))
+        mx, frac = _close(feats, ref, 3e-2 + 8e-3, 2e-2)             # VIT_ATOL + one bf16 ulp of O(1) tokens
+        assert frac == 0.0, (name, mx)

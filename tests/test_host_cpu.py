@@ -88,7 +88,10 @@ def test_pack_layout_and_lora_merge():
     for k, (shape, dt) in spec.items():
         assert tuple(packed[k].shape) == tuple(shape) and packed[k].dtype == dt, k
     assert torch.equal(packed["L0.qkv"][: cfg.num_attention_heads * 128], sd["model.layers.0.self_attn.q_proj.weight"])
-    assert torch.equal(packed["L1.gate_up"][cfg.intermediate_size:], sd["model.layers.1.mlp.up_proj.weight"])
+    # gate | up are tile-interleaved: 128-row tile j = gate rows 64j..64j+63, then the matching up rows
+    gu = packed["L1.gate_up"].view(cfg.intermediate_size // 64, 2, 64, cfg.hidden_size)
+    assert torch.equal(gu[:, 0].reshape(cfg.intermediate_size, -1), sd["model.layers.1.mlp.gate_proj.weight"])
+    assert torch.equal(gu[:, 1].reshape(cfg.intermediate_size, -1), sd["model.layers.1.mlp.up_proj.weight"])
     # LoRA merge == unmerged forward (y = W x + 2 B A x) up to bf16 rounding of the merged weight
     g = torch.Generator().manual_seed(0)
     r = 8
@@ -141,6 +144,9 @@ full = W.pack_llm_for_engine(cfg, W.synthetic_llm_state(cfg), 'cpu', 128)
 full.update(W.pack_vision_for_engine(cfg, W.synthetic_vision_state(cfg), 'cpu'))
 got = broadcast_weights(cfg, full if dist.get_rank() == 0 else None, 'cpu', 128, dist)
 assert set(got) == set(full) and all(torch.equal(got[k], full[k]) for k in full)
+# coalesced: <= 8 flat buffers carry every tensor, each view 256-byte aligned inside its buffer
+stores = {{t.untyped_storage().data_ptr() for t in got.values()}}
+assert len(stores) <= 8 and all((t.data_ptr() - t.untyped_storage().data_ptr()) % 256 == 0 for t in got.values())
 # static stream -> rank assignment: round-robin, every stream owned by exactly one rank
 streams = list(range(5)); mine = [s for s in streams if s % dist.get_world_size() == dist.get_rank()]
 cnt = torch.tensor([len(mine)]); dist.all_reduce(cnt); assert int(cnt) == 5

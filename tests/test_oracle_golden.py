@@ -139,3 +139,24 @@ def test_joint_embed_matches_reference(golden, tiny):
     torch.testing.assert_close(emb[is_v].float(), ref[is_v].float(), rtol=2e-2, atol=2e-2)   # as test_visual_embed_matches_reference
     logits = O.llama_forward(llm, cfg, ref, O.KVCache(cfg.num_hidden_layers))
     assert torch.equal(logits, golden["joint_logits"])
+
+
+def _se_state(golden, tiny):
+    cfg, llm, vis = tiny
+    sd = dict(llm)
+    w = sd["lm_head.weight"].clone()
+    w[cfg.frame_token_interval_id] = golden["se_lm_head_row"]     # see make_golden.craft_silent_lm_head
+    sd["lm_head.weight"] = w
+    return cfg, sd, vis
+
+
+def test_stream_evaluate_matches_reference(golden, tiny):
+    """models/modeling_live.py:44-168 on a two-turn sample: turn 1 takes the look-ahead branch (:110-141, trimmed
+    cache + appended frames), turn 2 the in-turn branch (:105-107).  Same four metrics as the reference's own method."""
+    cfg, sd, vis = _se_state(golden, tiny)
+    for thr in (0.0, 0.9):
+        got = O.stream_evaluate(sd, vis, cfg, golden["se_ids"], golden["se_labels"], golden["se_frames"],
+                                frame_token_interval_threshold=thr)
+        ref = golden[f"se_metrics_thr{thr}"]
+        torch.testing.assert_close(got[1:], ref[1:].float(), rtol=0, atol=0)
+        torch.testing.assert_close(got[0].log(), ref[0].float().log(), rtol=1e-5, atol=1e-5)

@@ -40,7 +40,8 @@ int attn_tc2_blk() {
   static int blk = 0;
   if (blk == 0) {
     const char* e = getenv("VLO_ATTN_BLK");
-    blk = (e != nullptr && atoi(e) == 64) ? 64 : 128;
+    (void)e;   // 64-key blocks were measured slower (per-block latency dominates): the kernel is built for 128
+    blk = 128;
   }
   return blk;
 }
@@ -222,12 +223,12 @@ static long long* attn_trace_buffer_for_launch() {
 }
 
 template <int BLK>
-static int launch_tc2(const AttnPlan& plan, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tq,
+static int launch_tc2(const AttnPlan& plan, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap* tq,
                       const AttnTc2Params& p, cudaStream_t stream) {
   auto kern = attn_tc2_kernel<BLK>;
   if (ensure_max_smem(reinterpret_cast<const void*>(kern), Tc2Cfg<BLK>::kSmemBytes)) return -1;
   prof_begin(PROF_ATTN, stream, plan.algo_bytes);
-  VLO_CUDA(launch_pdl(kern, dim3(plan.n_ctas), dim3(kTcThreads), Tc2Cfg<BLK>::kSmemBytes, stream, tk, tv, tq, p));
+  VLO_CUDA(launch_pdl(kern, dim3(plan.n_ctas), dim3(kTcThreads), Tc2Cfg<BLK>::kSmemBytes, stream, tk, tv, tq[0], tq[1], tq[2], p));
   prof_end(stream);
   count_launch();
   return 0;
@@ -236,10 +237,14 @@ static int launch_tc2(const AttnPlan& plan, const CUtensorMap& tk, const CUtenso
 static int attn_run_tc2(const AttnPlan& plan, const void* d_q, const void* d_k, const void* d_v, long long kv_rows,
                         void* d_out, int n_heads, int n_kv_heads, int head_dim, cudaStream_t stream) {
   const int blk = plan.blk;
-  CUtensorMap tk, tv, tq;
+  CUtensorMap tk, tv, tq[3];
   if (tmap_2d_sw128(d_k, static_cast<int>(kv_rows), kAttnHD, blk, 1, &tk) != 0) return -1;
   if (tmap_2d_sw128(d_v, static_cast<int>(kv_rows), kAttnHD, blk, 1, &tv) != 0) return -1;
-  if (tmap_q3d_sw128(d_q, plan.total_tokens, n_heads, n_heads / n_kv_heads, &tq) != 0) return -1;
+  const int G = n_heads / n_kv_heads;
+  for (int i = 0; i < 3; ++i) {   // Q boxes of 32 / 64 / 128 tile rows (key slicing); a box is at least one token
+    const int rows = std::max(32 << i, G);
+    if (tmap_q3d_sw128(d_q, plan.total_tokens, n_heads, G, &tq[i], rows) != 0) return -1;
+  }
   const float scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(head_dim)));
   AttnTc2Params p{};
   p.base.q = static_cast<const __nv_bfloat16*>(d_q);
@@ -254,8 +259,7 @@ static int attn_run_tc2(const AttnPlan& plan, const void* d_q, const void* d_k, 
   // V tile = MN-major B operand: 64-d halves one sub-tile apart (LBO), 8-key groups 1 KB apart (SBO)
   p.v_lbo = static_cast<uint32_t>(blk * 128);
   p.v_sbo = 1024u;
-  const int rc = blk == 64 ? launch_tc2<64>(plan, tk, tv, tq, p, stream) : launch_tc2<128>(plan, tk, tv, tq, p, stream);
-  if (rc) return rc;
+  if (launch_tc2<128>(plan, tk, tv, tq, p, stream)) return -1;
   if (plan.skip_merge) return 0;
   return launch_merge(plan, d_out, n_heads, n_kv_heads, scale_log2, stream);
 }

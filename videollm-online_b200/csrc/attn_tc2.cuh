@@ -14,6 +14,15 @@
 //     the block count allows (blk0 = split * nblk / n_splits), and the host deals the splits so that the grid
 //     fills the SMs: 8 kv heads x 18 splits = 144 CTAs for one stream (was 16 x 8 = 128 with equal-size splits).
 //
+//   * key slicing.  The softmax is MUFU-bound: one ex2 per (row, key), 4 lanes/clk per SM sub-partition, and a warp
+//     instruction costs the same with 11 live lanes as with 32.  A frame step has 44 live rows (11 tokens x 4 heads),
+//     an AR token 4, so with lane = row two (or three) of the four softmax warps idle while the others grind through
+//     128 columns.  Here the Q tile is replicated SL = 128 / pad(rows) times down the 128 MMA rows (pad = 32 / 64 / 128)
+//     and the softmax thread of lane = slice * pad + row handles only the 128 / SL keys of ITS slice of every block:
+//     all four sub-partitions work, each thread issues 128 / SL exponentials per block.  P columns outside a thread's
+//     slice stay zero (written once), so the unchanged O += P V accumulates per (slice, row) lane; the SL partial
+//     (m, l, O) rows of a query row are combined through shared memory in the epilogue.
+//
 //   warp 0      TMA producer: Q tile, then the K and V tiles of every block (K and V have their own full/empty pairs)
 //   warp 1      MMA issuer:   S_j = Q K_j^T -> TMEM S[j&1];  O += P_j V_j with P_j read from TMEM
 //   warps 2-5   softmax:      tcgen05.ld S row -> online softmax (lazy O rescale) -> tcgen05.st P_j -> epilogue
@@ -41,22 +50,240 @@ struct AttnTc2Params {
   long long* dbg;         // optional timeline buffer (VLO_ATTN_TRACE)
 };
 
-// D[tmem] (+)= A[tmem] * B[smem desc]; A: lane = row, 32-bit column = two consecutive K elements (K-major)
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+constexpr int kTc2CombStride = 132;   // floats per (slice, row) record in the combine buffer: O[128] | m | l | pad
+
+struct Tc2Ctx {
+  uint64_t *s_full, *s_empty, *p_full, *p_empty, *o_done;
+  uint32_t tS, tO, tP;
+  float* comb;            // shared-memory combine buffer (the K/V ring, free by then)
+  int nblk, blk0, G, kvh, split;
+};
+
+// Softmax / correction / epilogue role of one of the four softmax warps.  NC = keys per thread per block = 128 / SL;
+// lane L of the 128 TMEM lanes serves row r = L % NC of the item's tile and key slice L / NC.
+template <int NC>
+__device__ __forceinline__ void tc2_softmax_role(const AttnTc2Params& pp, const AttnItem& it, const Tc2Ctx& cx, int warp,
+                                                 int lane) {
+  constexpr int SL = 128 / NC;
+  const AttnParams& p = pp.base;
+  const int q = warp & 3;
+  const int L = q * 32 + lane;                 // TMEM lane
+  const int slice = L / NC, r = L % NC;        // key slice, tile row == t * G + g
+  const int rows = it.q_count * cx.G;
+  const int t = r / cx.G;
+  const bool valid = r < rows;
+  const bool warp_live = ((q * 32) % NC) < rows;    // any query row in this warp's 32 lanes?
+  const int lim = valid ? it.q_pos0 + t : -1;       // last visible key (causal with offset)
+  const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+  const uint32_t col0 = static_cast<uint32_t>(slice * NC);
+  const float c = p.scale_log2;
+  const int nblk = cx.nblk;
+  float m_ref = -INFINITY, l_run = 0.f;
+  if (SL > 1 && warp_live) {   // P columns of the other slices stay zero for the whole kernel
+    uint32_t z[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z[i] = 0u;
+#pragma unroll
+    for (int c0 = 0; c0 < 128; c0 += 32) tmem_st_x32(cx.tP + lane_addr + c0, z);
+    tmem_st_wait();
+  }
+  for (int j = 0; j < nblk; ++j) {
+    const int b = j & 1;
+    mbar_wait(&cx.s_full[b], (j >> 1) & 1);
+    tc_fence_after();
+    if (L == 0) VLO_TC_STAMP(2, 4 + 4 * j);
+    if (!warp_live) {  // no query row in these lanes: keep the barrier protocol going (their P / O rows stay
+                       // garbage; MMA rows are independent, they feed nothing but their own discarded O rows)
+      mbar_arrive(&cx.s_empty[b]);
+      mbar_wait(&cx.p_empty[b], ((j >> 1) & 1) ^ 1);
+      mbar_arrive(&cx.p_full[b]);
+      continue;
+    }
+    const int key0 = (cx.blk0 + j) * 128 + static_cast<int>(col0);
+    const bool need_mask = key0 + NC - 1 > it.q_pos0;  // slice reaches past the first query's limit
+    float sv[NC];
+    {
+      uint32_t su[NC];
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 32)
+        tmem_ld_x32(cx.tS + lane_addr + static_cast<uint32_t>(b * 128) + col0 + c0, *reinterpret_cast<uint32_t(*)[32]>(&su[c0]));
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < NC; ++i) sv[i] = __uint_as_float(su[i]);
+    }
+    tc_fence_before();
+    mbar_arrive(&cx.s_empty[b]);   // S[b] may be overwritten by block j+2
+    if (L == 0) VLO_TC_STAMP(2, 5 + 4 * j);
+    if (need_mask) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (key0 + i > lim) sv[i] = -INFINITY;
+    } else if (!valid) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) sv[i] = -INFINITY;
+    }
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < NC; i += 4) {
+      mx4[0] = fmaxf(mx4[0], sv[i]);
+      mx4[1] = fmaxf(mx4[1], sv[i + 1]);
+      mx4[2] = fmaxf(mx4[2], sv[i + 2]);
+      mx4[3] = fmaxf(mx4[3], sv[i + 3]);
+    }
+    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    // lazy rescale: keep the old reference max unless the new one is much larger
+    const float m_new = fmaxf(m_ref, mx);
+    const bool grow = (m_ref == -INFINITY) ? (m_new != -INFINITY) : ((m_new - m_ref) * c > kTcRescaleLog2);
+    const float m_use = grow ? m_new : m_ref;
+    const float alpha = (grow && m_ref != -INFINITY) ? exp2f((m_ref - m_new) * c) : 1.f;
+    if (__any_sync(0xffffffffu, alpha != 1.f)) {
+      // O of this warp's 32 lanes must be rescaled: wait until PV_{j-1} has landed in TMEM
+      mbar_wait(cx.o_done, (j - 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(cx.tO + lane_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+        tmem_st_x32(cx.tO + lane_addr + c0, v);
+      }
+      tmem_st_wait();
+      l_run *= alpha;
+    }
+    m_ref = m_use;
+    const float moff = (m_ref == -INFINITY) ? 0.f : m_ref * c;
+    // P = exp2(S c - m c) -> bf16 pairs -> TMEM; the P buffer must have been consumed by PV_{j-2} first
+    mbar_wait(&cx.p_empty[b], ((j >> 1) & 1) ^ 1);
+    tc_fence_after();
+    if (L == 0) VLO_TC_STAMP(2, 6 + 4 * j);
+    float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+    const float nmoff = -moff;
+    const uint32_t pcol = cx.tP + lane_addr + static_cast<uint32_t>(b * 64) + col0 / 2;
+    if constexpr (NC >= 64) {
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 64) {
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float p0 = ex2_approx(fmaf(sv[c0 + 2 * i], c, nmoff));
+          const float p1 = ex2_approx(fmaf(sv[c0 + 2 * i + 1], c, nmoff));
+          ps4[i & 3] += p0 + p1;
+          w[i] = pack_bf16(p0, p1);
+        }
+        tmem_st_x32(pcol + c0 / 2, w);
+      }
+    } else {
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = ex2_approx(fmaf(sv[2 * i], c, nmoff));
+        const float p1 = ex2_approx(fmaf(sv[2 * i + 1], c, nmoff));
+        ps4[i & 3] += p0 + p1;
+        w[i] = pack_bf16(p0, p1);
+      }
+      tmem_st_x16(pcol, w);
+    }
+    l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&cx.p_full[b]);
+    if (L == 0) VLO_TC_STAMP(2, 7 + 4 * j);
+  }
+  // ---- epilogue: partial (m, l, O) of this split; merged by attn_merge_kernel
+  mbar_wait(cx.o_done, (nblk - 1) & 1);
+  tc_fence_after();
+  if (L == 0) VLO_TC_STAMP(2, 1);
+  float w_self = 1.f;
+  if constexpr (SL > 1) {
+    // slices >= 1 park their (O, m, l) rows in shared memory; slice 0 folds them into its own row
+    float* rec = cx.comb + static_cast<size_t>((slice > 0 ? slice - 1 : 0) * NC + r) * kTc2CombStride;
+    // NOTE: tcgen05.ld is .sync.aligned - every lane of the warp must execute it: the TMEM loads are guarded by
+    // warp-uniform conditions only (slice, warp_live); `valid` guards nothing but the stores.
+    if (slice > 0 && warp_live) {
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(cx.tO + lane_addr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(rec + c0 + 4 * i) = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                        __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      }
+      if (valid) {
+        rec[128] = m_ref;
+        rec[129] = l_run;
+      }
+    }
+    asm volatile("bar.sync 1, 128;\n" ::: "memory");   // the four softmax warps
+    if (slice == 0 && valid) {
+      float m_all = m_ref;
+#pragma unroll
+      for (int s2 = 1; s2 < SL; ++s2) m_all = fmaxf(m_all, cx.comb[static_cast<size_t>((s2 - 1) * NC + r) * kTc2CombStride + 128]);
+      w_self = (m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_all) * c);
+      l_run *= w_self;
+#pragma unroll
+      for (int s2 = 1; s2 < SL; ++s2) {
+        const float* o2 = cx.comb + static_cast<size_t>((s2 - 1) * NC + r) * kTc2CombStride;
+        const float m2 = o2[128];
+        l_run += (m2 == -INFINITY) ? 0.f : o2[129] * exp2f((m2 - m_all) * c);
+      }
+      m_ref = m_all;
+    }
+  }
+  const size_t slot = static_cast<size_t>(it.ws_slot0) + (static_cast<size_t>(cx.kvh) * it.n_splits + cx.split) * rows + r;
+  if (slice == 0 && warp_live) {   // warp-uniform guard around the TMEM loads (see above)
+    float* dst = p.ws_o + slot * kAttnHD;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_x32(cx.tO + lane_addr + c0, v);
+      tmem_ld_wait();
+      if (valid) {
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]) * w_self;
+        if constexpr (SL > 1) {
+#pragma unroll
+          for (int s2 = 1; s2 < SL; ++s2) {
+            const float* o2 = cx.comb + static_cast<size_t>((s2 - 1) * NC + r) * kTc2CombStride;
+            const float m2 = o2[128];
+            const float w2 = (m2 == -INFINITY) ? 0.f : exp2f((m2 - m_ref) * c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 x = *reinterpret_cast<const float4*>(o2 + c0 + 4 * i);
+              o[4 * i] = fmaf(x.x, w2, o[4 * i]);
+              o[4 * i + 1] = fmaf(x.y, w2, o[4 * i + 1]);
+              o[4 * i + 2] = fmaf(x.z, w2, o[4 * i + 2]);
+              o[4 * i + 3] = fmaf(x.w, w2, o[4 * i + 3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(dst + c0 + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      }
+    }
+    if (valid) {
+      p.ws_ml[slot * 2] = m_ref;
+      p.ws_ml[slot * 2 + 1] = l_run;
+    }
+  }
+  if (L == 0) VLO_TC_STAMP(2, 2);
+  tc_fence_before();
 }
 
-// grid = (n_ctas); block = 192.
+// grid = (n_ctas); block = 192.  tm_q32 / tm_q64 / tm_q128: Q maps whose box holds 32 / 64 / 128 tile rows.
 template <int BLK>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                const __grid_constant__ CUtensorMap tm_q, const AttnTc2Params pp) {
+                const __grid_constant__ CUtensorMap tm_q32, const __grid_constant__ CUtensorMap tm_q64,
+                const __grid_constant__ CUtensorMap tm_q128, const AttnTc2Params pp) {
+  static_assert(BLK == 128, "key slicing assumes 128-key blocks");
   using C = Tc2Cfg<BLK>;
   constexpr int NS = C::kStages;
   const AttnParams& p = pp.base;
@@ -87,7 +314,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
-    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_q32);
+    tma_prefetch_desc(&tm_q64);
+    tma_prefetch_desc(&tm_q128);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -112,6 +341,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   pdl_trigger();  // after the TMEM allocation (see gemm_ws.cuh)
 
   const int G = p.n_heads / p.n_kv_heads;
+  // key slicing: pad = rows of one Q-tile copy (32 / 64 / 128, >= the live rows and >= G), SL = 128 / pad copies
+  const int rows_live = it.q_count * G;
+  const int need_rows = rows_live > G ? rows_live : G;
+  const int pad = need_rows <= 32 ? 32 : (need_rows <= 64 ? 64 : 128);
   const int kv_end = it.q_pos0 + it.q_count;
   const int nblk_total = (kv_end + BLK - 1) / BLK;
   const int blk0 = static_cast<int>((static_cast<long long>(split) * nblk_total) / it.n_splits);
@@ -155,9 +388,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     if (warp == 0) {
       if (lane == 0) {
         // ------------------------------------------------------------ TMA producer
+        // Q tile: 128 / pad copies of the pad rows (row = token * G + head), one 3-D box per 64-dim half and copy
+        const CUtensorMap* tq = pad == 32 ? &tm_q32 : (pad == 64 ? &tm_q64 : &tm_q128);
         mbar_arrive_expect_tx(q_ready, C::kQBytes);
-        tma_load_3d(q_tile, &tm_q, q_ready, 0, kvh * G, it.q_tok0, kEvictNormal);
-        tma_load_3d(q_tile + kTcSub, &tm_q, q_ready, 64, kvh * G, it.q_tok0, kEvictNormal);
+        for (int cp = 0; cp < 128 / pad; ++cp) {
+          tma_load_3d(q_tile + cp * pad * 128, tq, q_ready, 0, kvh * G, it.q_tok0, kEvictNormal);
+          tma_load_3d(q_tile + kTcSub + cp * pad * 128, tq, q_ready, 64, kvh * G, it.q_tok0, kEvictNormal);
+        }
         for (int j = pre; j < nblk; ++j) {
           const int s = j % NS;
           const uint32_t ph = (j / NS) & 1;
@@ -217,137 +454,14 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       }
     } else {
       // -------------------------------------------------------------- softmax / correction / epilogue warps
-      const int q = warp & 3;
-      const int r = q * 32 + lane;       // TMEM lane == tile row == t * G + g
-      const int t = r / G;
-      const bool valid = r < it.q_count * G;
-      const bool warp_live = q * 32 < it.q_count * G;   // any query row in this warp's 32 lanes?
-      const int lim = valid ? it.q_pos0 + t : -1;       // last visible key (causal with offset)
-      const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-      const float c = p.scale_log2;
-      float m_ref = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < nblk; ++j) {
-        const int b = j & 1;
-        mbar_wait(&s_full[b], (j >> 1) & 1);
-        tc_fence_after();
-        if (r == 0) VLO_TC_STAMP(2, 4 + 4 * j);
-        if (!warp_live) {  // no query row in these lanes: keep the barrier protocol going (their P / O rows stay
-                           // garbage; MMA rows are independent, they feed nothing but their own discarded O rows)
-          mbar_arrive(&s_empty[b]);
-          mbar_wait(&p_empty[b], ((j >> 1) & 1) ^ 1);
-          mbar_arrive(&p_full[b]);
-          continue;
-        }
-        const int key0 = (blk0 + j) * BLK;
-        const bool need_mask = key0 + BLK - 1 > it.q_pos0;  // block reaches past the first query's limit
-        float sv[BLK];
-#pragma unroll
-        for (int c0 = 0; c0 < BLK; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(tS + lane_addr + b * 128 + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sv[c0 + i] = __uint_as_float(v[i]);
-        }
-        tc_fence_before();
-        mbar_arrive(&s_empty[b]);   // S[b] may be overwritten by block j+2
-        if (r == 0) VLO_TC_STAMP(2, 5 + 4 * j);
-        if (need_mask) {
-#pragma unroll
-          for (int i = 0; i < BLK; ++i)
-            if (key0 + i > lim) sv[i] = -INFINITY;
-        } else if (!valid) {
-#pragma unroll
-          for (int i = 0; i < BLK; ++i) sv[i] = -INFINITY;
-        }
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int i = 0; i < BLK; i += 4) {
-          mx4[0] = fmaxf(mx4[0], sv[i]);
-          mx4[1] = fmaxf(mx4[1], sv[i + 1]);
-          mx4[2] = fmaxf(mx4[2], sv[i + 2]);
-          mx4[3] = fmaxf(mx4[3], sv[i + 3]);
-        }
-        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        // lazy rescale: keep the old reference max unless the new one is much larger
-        const float m_new = fmaxf(m_ref, mx);
-        const bool grow = (m_ref == -INFINITY) ? (m_new != -INFINITY) : ((m_new - m_ref) * c > kTcRescaleLog2);
-        const float m_use = grow ? m_new : m_ref;
-        const float alpha = (grow && m_ref != -INFINITY) ? exp2f((m_ref - m_new) * c) : 1.f;
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
-          // O of this warp's 32 lanes must be rescaled: wait until PV_{j-1} has landed in TMEM
-          mbar_wait(o_done, (j - 1) & 1);
-          tc_fence_after();
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_x32(tO + lane_addr + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_x32(tO + lane_addr + c0, v);
-          }
-          tmem_st_wait();
-          l_run *= alpha;
-        }
-        m_ref = m_use;
-        const float moff = (m_ref == -INFINITY) ? 0.f : m_ref * c;
-        // P = exp2(S c - m c) -> bf16 pairs -> TMEM; the P buffer must have been consumed by PV_{j-2} first
-        mbar_wait(&p_empty[b], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        if (r == 0) VLO_TC_STAMP(2, 6 + 4 * j);
-        float ps4[4] = {0.f, 0.f, 0.f, 0.f};
-        const float nmoff = -moff;
-#pragma unroll
-        for (int c0 = 0; c0 < BLK; c0 += 64) {
-          uint32_t w[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float p0 = ex2_approx(fmaf(sv[c0 + 2 * i], c, nmoff));
-            const float p1 = ex2_approx(fmaf(sv[c0 + 2 * i + 1], c, nmoff));
-            ps4[i & 3] += p0 + p1;
-            w[i] = pack_bf16(p0, p1);
-          }
-          tmem_st_x32(tP + lane_addr + static_cast<uint32_t>(b * 64 + c0 / 2), w);
-        }
-        l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[b]);
-        if (r == 0) VLO_TC_STAMP(2, 7 + 4 * j);
-      }
-      // ---- epilogue: partial (m, l, O) of this split; merged by attn_merge_kernel
-      mbar_wait(o_done, (nblk - 1) & 1);
-      tc_fence_after();
-      if (r == 0) VLO_TC_STAMP(2, 1);
-      const int rows = it.q_count * G;
-      const size_t slot = static_cast<size_t>(it.ws_slot0) + (static_cast<size_t>(kvh) * it.n_splits + split) * rows + r;
-      if (warp_live) {
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 64) {
-          uint32_t v0[32], v1[32];
-          tmem_ld_x32(tO + lane_addr + c0, v0);
-          tmem_ld_x32(tO + lane_addr + c0 + 32, v1);
-          tmem_ld_wait();
-          if (valid) {
-            float4* dst = reinterpret_cast<float4*>(p.ws_o + slot * kAttnHD + c0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              dst[i] = make_float4(__uint_as_float(v0[4 * i]), __uint_as_float(v0[4 * i + 1]), __uint_as_float(v0[4 * i + 2]),
-                                   __uint_as_float(v0[4 * i + 3]));
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              dst[8 + i] = make_float4(__uint_as_float(v1[4 * i]), __uint_as_float(v1[4 * i + 1]), __uint_as_float(v1[4 * i + 2]),
-                                       __uint_as_float(v1[4 * i + 3]));
-          }
-        }
-        if (valid) {
-          p.ws_ml[slot * 2] = m_ref;
-          p.ws_ml[slot * 2 + 1] = l_run;
-        }
-      }
-      if (r == 0) VLO_TC_STAMP(2, 2);
-      tc_fence_before();
+      Tc2Ctx cx;
+      cx.s_full = s_full, cx.s_empty = s_empty, cx.p_full = p_full, cx.p_empty = p_empty, cx.o_done = o_done;
+      cx.tS = tS, cx.tO = tO, cx.tP = tP;
+      cx.comb = reinterpret_cast<float*>(kv_tile);
+      cx.nblk = nblk, cx.blk0 = blk0, cx.G = G, cx.kvh = kvh, cx.split = split;
+      if (pad == 32) tc2_softmax_role<32>(pp, it, cx, warp, lane);
+      else if (pad == 64) tc2_softmax_role<64>(pp, it, cx, warp, lane);
+      else tc2_softmax_role<128>(pp, it, cx, warp, lane);
     }
   }
   __syncthreads();

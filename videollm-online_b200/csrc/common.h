@@ -123,6 +123,10 @@ struct GemmWsCall {
 int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_planes, int x_tiles = 1);
 int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream);
 
+// ---- stream-K GEMM with the fused finisher epilogue (gemm_wsf.cuh / gemm.cu); args struct defined in gemm_wsf.cuh
+struct GemmWsfArgs;
+int gemm_wsf_launch(const GemmWsfArgs& a, const void* w, const void* x, int epi, cudaStream_t stream);
+
 // ---- attention (attn.cu) ------------------------------------------------------------
 struct AttnSeq {
   int q_tok0;          // first packed token of the sequence
@@ -159,6 +163,6 @@ int attn_run(const AttnPlan& plan, const void* d_q, const void* d_k, const void*
 
 // 2D TMA map over a row-major 16-bit matrix [rows, k], box 64 x box_rows, 128-byte swizzle (cached).
 int tmap_2d_sw128(const void* ptr, int rows, int k, int box_rows, int fmt, CUtensorMap* out);
-int tmap_q3d_sw128(const void* ptr, int n_tok, int n_heads, int G, CUtensorMap* out);  // attention Q tile (see gemm.cu)
+int tmap_q3d_sw128(const void* ptr, int n_tok, int n_heads, int G, CUtensorMap* out, int box_rows = 128);  // attention Q tile (see gemm.cu)
 
 }  // namespace vlo

@@ -190,7 +190,10 @@ __global__ void __launch_bounds__(64) qkv_rope_append_kernel(const QkvRopeParams
 
 // ---------------------------------------------------------------------------------------------
 // gate/up split-K fix-up + SwiGLU:  act = bf16(bf16(silu(g)) * u)      (LlamaMLP, :182-184)
-// part columns [0, I) = gate, [I, 2I) = up.   grid-stride over T*I/2 pairs.
+// The fused gate|up weight is stored tile-interleaved: 128-row tile j = gate rows of features 64j..64j+63 followed by
+// the matching up rows (so one tile holds both operands of 64 activations: gemm_wsf.cuh fuses this kernel into the
+// GEMM's finisher; this stand-alone version is the VLO_FUSE=0 fallback).  part column of feature i: gate
+// (i/64)*128 + i%64, up = gate + 64.   grid-stride over T*I/4 quads.
 struct SwigluParams {
   const float* part;
   int n_splits;  // > 0 planes, < 0 stream-K
@@ -208,22 +211,22 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const SwigluParams p) {
   if (idx0 < n4) {
     const long long e = idx0 * 4;
     t0 = static_cast<int>(e / p.I), c0 = static_cast<int>(e % p.I);
-    ng0 = p.n_splits > 0 ? p.n_splits : sk_planes(c0 >> 7, p.sk);
-    nu0 = p.n_splits > 0 ? p.n_splits : sk_planes((p.I + c0) >> 7, p.sk);
+    ng0 = p.n_splits > 0 ? p.n_splits : sk_planes(c0 >> 6, p.sk);
+    nu0 = ng0;
   }
   pdl_wait();
   for (long long idx = idx0; idx < n4; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long e = idx * 4;
     const bool first = idx == idx0;
     const int t = first ? t0 : static_cast<int>(e / p.I), i = first ? c0 : static_cast<int>(e % p.I);
-    const float* pg = p.part + static_cast<size_t>(t) * 2 * p.I + i;
-    const int ng = first ? ng0 : (p.n_splits > 0 ? p.n_splits : sk_planes(i >> 7, p.sk));
-    const int nu = first ? nu0 : (p.n_splits > 0 ? p.n_splits : sk_planes((p.I + i) >> 7, p.sk));
+    const float* pg = p.part + static_cast<size_t>(t) * 2 * p.I + (i >> 6) * 128 + (i & 63);
+    const int ng = first ? ng0 : (p.n_splits > 0 ? p.n_splits : sk_planes(i >> 6, p.sk));
+    const int nu = ng;
     float4 ga[kFixMaxPlanes], ua[kFixMaxPlanes];
 #pragma unroll
     for (int s = 0; s < kFixMaxPlanes; ++s) {
       ga[s] = (s < ng) ? *reinterpret_cast<const float4*>(pg + s * p.split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
-      ua[s] = (s < nu) ? *reinterpret_cast<const float4*>(pg + s * p.split_stride + p.I) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ua[s] = (s < nu) ? *reinterpret_cast<const float4*>(pg + s * p.split_stride + 64) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float g[4] = {0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll

@@ -10,7 +10,9 @@
 #include "common.h"
 #include "decoder_kernels.cuh"
 #include "gemm.cuh"
+#include "gemm_wsf.cuh"
 #include "vit_kernels.cuh"
+#include "vit_attn_tc.cuh"
 #include "vlo_b200.h"
 
 using namespace vlo;
@@ -68,6 +70,9 @@ struct vlo_engine {
        *logits = nullptr;
   float* part = nullptr;
   size_t part_elems = 0;
+  int* sk_flags = nullptr;          // stream-K arrival counters of the fused-finisher GEMMs (zero between launches)
+  bf16* bench_kv = nullptr;         // scratch K / V rows for vlo_bench_gemm's fused QKV epilogue
+  uint8_t* bench_meta = nullptr;    // tok_pos | tok_kvrow of the micro-loop
   uint8_t* attn_ws = nullptr;
   uint8_t* meta_dev = nullptr;  // tok_pos | tok_kvrow | last_index | first_rows
   size_t meta_bytes = 0;
@@ -155,6 +160,32 @@ int gemm_partial(vlo_engine* e, const bf16* w, int n_out, const bf16* x, int T, 
   return gemm_ws_launch(c, st);
 }
 
+// Fused-finisher switch (default on): VLO_FUSE=0 falls back to stream-K planes + separate fix-up kernels (A/B checks).
+bool fuse_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLO_FUSE");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// stream-K GEMM whose finisher CTAs apply the fix-up themselves (gemm_wsf.cuh); `a` carries the epilogue's operands
+int gemm_fused(vlo_engine* e, GemmWsfArgs& a, int epi, const bf16* w, int n_out, const bf16* x, int T, int k, cudaStream_t st) {
+  int planes = 1;
+  gemm_ws_plan(n_out, k, 0, dec_ctas(), &a.sk, &planes);
+  VLO_CHECK(static_cast<size_t>(std::max(1, planes - 1)) * T * n_out <= e->part_elems, "stream-K workspace too small");
+  VLO_CHECK((n_out + 127) / 128 <= 4096, "stream-K flag array too small");
+  a.rows_w = n_out;
+  a.rows_x = T;
+  a.k = k;
+  a.planes = e->part;
+  a.plane_stride = static_cast<long long>(T) * n_out;
+  a.flags = e->sk_flags;
+  a.hint_w = kEvictFirst;
+  return gemm_wsf_launch(a, w, x, epi, st);
+}
+
 // whole-tile persistent GEMM with the 16-bit epilogue: out[T, n_out] = act(x W^T + bias)
 int gemm_ws_store16(int fmt, const void* w, int n_out, const void* x, int T, int k, void* out, int ld, const float* bias,
                     int act, cudaStream_t st) {
@@ -231,6 +262,20 @@ inline long long kv_rows_per_layer(const vlo_config& c) {
   return static_cast<long long>(c.max_streams) * c.num_kv_heads * c.max_kv_tokens;
 }
 
+// Every entry point that touches the device runs on the engine's GPU whatever the caller's current device is
+// (one process may own engines on several GPUs); the previous device is restored on return.
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DevGuard(const vlo_engine* e) {
+    if (e == nullptr) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != e->device) switched = cudaSetDevice(e->device) == cudaSuccess;
+  }
+  ~DevGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 int check_stream(vlo_engine* e, int sid) {
   if (e == nullptr) return fail("null engine");
   if (sid < 0 || sid >= e->cfg.max_streams || !e->stream_open[sid]) return fail("invalid stream id " + std::to_string(sid));
@@ -241,8 +286,13 @@ int check_stream(vlo_engine* e, int sid) {
 
 extern "C" {
 
+static int engine_init(vlo_engine* e);
+
 int vlo_engine_create(const vlo_config* cfg, int device, vlo_engine** out) {
   VLO_CHECK(cfg != nullptr && out != nullptr, "null argument");
+  *out = nullptr;
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
   VLO_CUDA(cudaSetDevice(device));
   if (!vlo_device_supported(device)) return fail("device is not an sm_100 (Blackwell) GPU; there is no fallback path");
   const vlo_config& c = *cfg;
@@ -267,8 +317,20 @@ int vlo_engine_create(const vlo_config* cfg, int device, vlo_engine** out) {
   e->n_frame_tokens = (c.frame_token_cls ? 1 : 0) + c.pool_h * c.pool_w;
   e->kv_len.assign(c.max_streams, 0);
   e->stream_open.assign(c.max_streams, 0);
-  *out = e;
+  const int rc = engine_init(e);
+  if (rc != 0) {   // no half-built engine escapes: free what was allocated, keep the error text
+    const std::string msg = last_error();
+    vlo_engine_destroy(e);
+    set_error(msg);
+  } else {
+    *out = e;
+  }
+  if (prev_dev >= 0 && prev_dev != device) cudaSetDevice(prev_dev);
+  return rc;
+}
 
+static int engine_init(vlo_engine* e) {
+  const vlo_config& c = e->cfg;
   const int T = c.max_step_tokens;
   const int H = c.hidden_size;
   // KV cache, zero-initialised once: attention may touch (masked) rows past kv_len, they must be finite.
@@ -285,6 +347,9 @@ int vlo_engine_create(const vlo_config* cfg, int device, vlo_engine** out) {
   const int widest = std::max(std::max(e->qkv_width, 2 * c.intermediate_size), H);
   e->part_elems = static_cast<size_t>(8) * T * widest;  // stream-K needs <= kb/floor(U/G) + 2 planes (<= 4 in practice)
   if (dev_alloc_t(e, &e->part, e->part_elems)) return -1;
+  if (dev_alloc_t(e, &e->sk_flags, 4096, true)) return -1;
+  if (dev_alloc_t(e, &e->bench_kv, static_cast<size_t>(2) * c.num_kv_heads * T * c.head_dim, true)) return -1;
+  if (dev_alloc(e, reinterpret_cast<void**>(&e->bench_meta), align256(sizeof(int) * T) + align256(sizeof(long long) * T), true)) return -1;
   const size_t aws = attn_ws_bytes(T, c.max_streams, c.num_heads, c.num_kv_heads);
   if (dev_alloc(e, reinterpret_cast<void**>(&e->attn_ws), aws, false)) return -1;
   e->meta_bytes = align256(sizeof(int) * T) * 3 + align256(sizeof(long long) * T);
@@ -445,6 +510,7 @@ int vlo_kv_truncate(vlo_engine* e, int sid, int new_len) {
   return 0;
 }
 int vlo_kv_fill_synthetic(vlo_engine* e, int sid, int n_tokens, uint64_t seed, void* cuda_stream) {
+  DevGuard dev_guard(e);
   if (check_stream(e, sid)) return -1;
   const vlo_config& c = e->cfg;
   VLO_CHECK(n_tokens >= 0 && n_tokens <= c.max_kv_tokens, "kv_fill: n_tokens out of range");
@@ -463,6 +529,7 @@ int vlo_kv_fill_synthetic(vlo_engine* e, int sid, int n_tokens, uint64_t seed, v
   return 0;
 }
 int vlo_kv_read(vlo_engine* e, int sid, int layer, int is_v, void* d_out, void* cuda_stream) {
+  DevGuard dev_guard(e);
   if (check_stream(e, sid)) return -1;
   const vlo_config& c = e->cfg;
   VLO_CHECK(layer >= 0 && layer < c.num_layers, "layer out of range");
@@ -475,6 +542,7 @@ int vlo_kv_read(vlo_engine* e, int sid, int layer, int is_v, void* d_out, void* 
   return 0;
 }
 int vlo_kv_write(vlo_engine* e, int sid, int layer, int is_v, const void* d_in, int n_tokens, void* cuda_stream) {
+  DevGuard dev_guard(e);
   if (check_stream(e, sid)) return -1;
   const vlo_config& c = e->cfg;
   VLO_CHECK(layer >= 0 && layer < c.num_layers, "layer out of range");
@@ -488,8 +556,30 @@ int vlo_kv_write(vlo_engine* e, int sid, int layer, int is_v, const void* d_in, 
   return 0;
 }
 
+int vlo_kv_copy_prefix(vlo_engine* e, int src_sid, int dst_sid, int n_tokens, void* cuda_stream) {
+  DevGuard dev_guard(e);
+  if (check_stream(e, src_sid) || check_stream(e, dst_sid)) return -1;
+  const vlo_config& c = e->cfg;
+  VLO_CHECK(src_sid != dst_sid, "kv_copy_prefix: source and destination streams must differ");
+  VLO_CHECK(n_tokens >= 0 && n_tokens <= e->kv_len[src_sid], "kv_copy_prefix: n_tokens exceeds the source length");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const size_t per_stream = static_cast<size_t>(c.num_kv_heads) * c.max_kv_tokens * c.head_dim;
+  const size_t pitch = static_cast<size_t>(c.max_kv_tokens) * c.head_dim * sizeof(bf16);
+  if (n_tokens > 0)
+    for (int l = 0; l < c.num_layers; ++l)
+      for (int v = 0; v < 2; ++v) {
+        bf16* base = kv_layer_base(e, l, v);
+        VLO_CUDA(cudaMemcpy2DAsync(base + static_cast<size_t>(dst_sid) * per_stream, pitch, base + static_cast<size_t>(src_sid) * per_stream,
+                                   pitch, static_cast<size_t>(n_tokens) * c.head_dim * sizeof(bf16), c.num_kv_heads,
+                                   cudaMemcpyDeviceToDevice, st));
+      }
+  e->kv_len[dst_sid] = n_tokens;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ vision
 int vlo_connector(vlo_engine* e, const void* d_tokens, int n_rows, void* d_out, void* cuda_stream) {
+  DevGuard dev_guard(e);
   VLO_CHECK(e != nullptr && e->finalized && e->has_connector, "connector weights not loaded");
   const vlo_config& c = e->cfg;
   const int cap = std::max(1, c.max_vit_batch) * std::max(1, e->n_frame_tokens);
@@ -511,6 +601,7 @@ int vlo_connector(vlo_engine* e, const void* d_tokens, int n_rows, void* d_out, 
 }
 
 int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, float* d_vit_tokens, void* cuda_stream) {
+  DevGuard dev_guard(e);
   VLO_CHECK(e != nullptr && e->finalized && e->has_vit, "vision tower weights not loaded");
   const vlo_config& c = e->cfg;
   VLO_CHECK(B > 0 && B <= c.max_vit_batch, "vit_encode: batch exceeds max_vit_batch");
@@ -544,8 +635,17 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     if (gemm_launch(g, st)) return -1;
   }
   if (ensure_max_smem(reinterpret_cast<const void*>(vit_attn_kernel), kVitSmemBytes)) return -1;
+  // attention kernel generation: tcgen05 (vit_attn_tc.cuh) whenever the frame's K / V fit its resident ring;
+  // VLO_VIT_ATTN=1 forces the mma.sync kernel (A/B checks)
+  static int vit_attn_gen = -1;
+  if (vit_attn_gen < 0) {
+    const char* ev = getenv("VLO_VIT_ATTN");
+    vit_attn_gen = (ev != nullptr && ev[0] == '1') ? 1 : 2;
+  }
+  const bool attn_tc = vit_attn_gen == 2 && (P + kVitTcBlk - 1) / kVitTcBlk <= kVitTcMaxBlk;
   CUtensorMap tm_qkv;
-  if (tmap_2d_sw128(e->v_qkv, rows, 3 * C, kVitBlk, FMT_F16, &tm_qkv)) return -1;
+  if (tmap_2d_sw128(e->v_qkv, rows, 3 * C, attn_tc ? kVitTcBlk : kVitBlk, FMT_F16, &tm_qkv)) return -1;
+  if (attn_tc && ensure_max_smem(reinterpret_cast<const void*>(vit_attn_tc_kernel), kVitTcSmemBytes)) return -1;
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // head_dim 64
   // Trunk GEMMs on the persistent swap-AB kernel (weights ride MMA-M, the 576*B token rows are tiled along
   // MMA-N): QKV and fc1 run whole tiles with the fused bias / GELU fp16 epilogue; out_proj and fc2 (few
@@ -648,8 +748,12 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     SkCall sc{};
     if (tiles_gemm(e->v_xn, v.qkv_w, 3 * C, C, e->v_qkv, v.qkv_b, ACT_NONE)) return -1;
     prof_begin(PROF_VIT_ATTN, st, 4.0 * rows * C * 2);
-    VLO_CUDA(launch_pdl(vit_attn_kernel, dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), dim3(kVitThreads), kVitSmemBytes, st,
-                        tm_qkv, e->v_attn, P, C, scale_log2));
+    if (attn_tc)
+      VLO_CUDA(launch_pdl(vit_attn_tc_kernel, dim3((P + kVitTcBlk - 1) / kVitTcBlk, c.vit_heads, B), dim3(kVitTcThreads),
+                          kVitTcSmemBytes, st, tm_qkv, e->v_attn, P, C, scale_log2));
+    else
+      VLO_CUDA(launch_pdl(vit_attn_kernel, dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), dim3(kVitThreads), kVitSmemBytes, st,
+                          tm_qkv, e->v_attn, P, C, scale_log2));
     prof_end(st);
     count_launch();
     if (partial_gemm(e->v_attn, v.out_w, C, &sc)) return -1;
@@ -703,6 +807,7 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
 
 // ------------------------------------------------------------------------------ decoder
 int vlo_embed_tokens(vlo_engine* e, const int64_t* d_ids, int n, void* d_out, void* cuda_stream) {
+  DevGuard dev_guard(e);
   VLO_CHECK(e != nullptr && e->finalized && e->has_decoder, "decoder weights not loaded");
   VLO_CHECK(n > 0, "embed_tokens: n must be positive");
   embed_rows_kernel<<<n, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
@@ -716,6 +821,7 @@ int vlo_embed_tokens(vlo_engine* e, const int64_t* d_ids, int n, void* d_out, vo
 int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const int32_t* h_q_lens,
                  const int64_t* d_row_ids, const void* d_embeds, void* d_last_logits, vlo_decision* d_decisions,
                  int interval_id, void* cuda_stream) {
+  DevGuard dev_guard(e);
   VLO_CHECK(e != nullptr && e->finalized && e->has_decoder, "decoder weights not loaded");
   const vlo_config& c = e->cfg;
   VLO_CHECK(n_seqs > 0 && n_seqs <= c.max_streams, "step: n_seqs out of range");
@@ -798,6 +904,36 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
   for (int l = 0; l < c.num_layers; ++l) {
     const DecLayer& d = e->dec[l];
     SkInfo sk{};
+    const bool is_last = (l == c.num_layers - 1);
+    if (fuse_enabled()) {
+      // 8 launches per layer: the stream-K finisher CTAs apply RoPE + KV append / residual add / SwiGLU themselves
+      GemmWsfArgs a{};
+      a.cos_tab = e->rope_cos;
+      a.sin_tab = e->rope_sin;
+      a.tok_pos = d_tok_pos;
+      a.tok_kvrow = d_tok_kvrow;
+      a.kv_head_stride = c.max_kv_tokens;
+      a.q_out = e->q;
+      a.k_cache = kv_layer_base(e, l, 0);
+      a.v_cache = kv_layer_base(e, l, 1);
+      a.n_heads = c.num_heads;
+      a.n_kv_heads = c.num_kv_heads;
+      if (gemm_fused(e, a, WSF_QKV, d.qkv, e->qkv_width, e->xn, T, H, st)) return -1;
+      if (attn_run(plan, e->q, kv_layer_base(e, l, 0), kv_layer_base(e, l, 1), kv_rows_per_layer(c), e->attn_out,
+                   c.num_heads, c.num_kv_heads, c.head_dim, st))
+        return -1;
+      GemmWsfArgs r{};
+      r.h = e->h;
+      if (gemm_fused(e, r, WSF_RESID, d.o, H, e->attn_out, T, attn_width, st)) return -1;
+      if (resid_norm(nullptr, 0, d.post_norm, false)) return -1;
+      GemmWsfArgs g{};
+      g.act = e->act;
+      g.I = c.intermediate_size;
+      if (gemm_fused(e, g, WSF_SWIGLU, d.gate_up, 2 * c.intermediate_size, e->xn, T, H, st)) return -1;
+      if (gemm_fused(e, r, WSF_RESID, d.down, H, e->act, T, c.intermediate_size, st)) return -1;
+      if (resid_norm(nullptr, 0, is_last ? e->final_norm : e->dec[l + 1].in_norm, is_last)) return -1;
+      continue;
+    }
     // fused q|k|v projection -> partials; fix-up + RoPE + in-place KV append
     if (gemm_partial(e, d.qkv, e->qkv_width, e->xn, T, H, &sk, st)) return -1;
     {
@@ -840,7 +976,6 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
       count_launch();
     }
     if (gemm_partial(e, d.down, H, e->act, T, c.intermediate_size, &sk, st)) return -1;
-    const bool is_last = (l == c.num_layers - 1);
     if (resid_norm(&sk, static_cast<long long>(T) * H, is_last ? e->final_norm : e->dec[l + 1].in_norm, is_last)) return -1;
   }
   // ---- last-position lm_head + on-device decision
@@ -869,6 +1004,7 @@ int vlo_step(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const int32
 // per launch then carries no per-launch event overhead and includes the PDL overlap the step really has.
 int vlo_bench_attn(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, int n_tok, int iters, int skip_merge,
                    double* h_algo_bytes_per_launch, void* cuda_stream) {
+  DevGuard dev_guard(e);
   VLO_CHECK(e != nullptr && e->finalized && e->has_decoder, "decoder weights not loaded");
   const vlo_config& c = e->cfg;
   VLO_CHECK(n_seqs > 0 && n_seqs <= c.max_streams && n_tok > 0 && n_seqs * n_tok <= c.max_step_tokens, "bench_attn: sizes");
@@ -901,6 +1037,7 @@ int vlo_bench_attn(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, int n
 
 int vlo_bench_gemm(vlo_engine* e, int n_tok, int iters, double* h_algo_bytes_per_iter, int* h_launches_per_iter,
                    void* cuda_stream) {
+  DevGuard dev_guard(e);
   VLO_CHECK(e != nullptr && e->finalized && e->has_decoder, "decoder weights not loaded");
   const vlo_config& c = e->cfg;
   VLO_CHECK(n_tok > 0 && n_tok <= c.max_step_tokens, "bench_gemm: n_tok out of range");
@@ -925,6 +1062,7 @@ int vlo_bench_gemm(vlo_engine* e, int n_tok, int iters, double* h_algo_bytes_per
 }
 
 int vlo_last_step_hidden(vlo_engine* e, void* d_hidden, void* cuda_stream) {
+  DevGuard dev_guard(e);
   VLO_CHECK(e != nullptr && e->last_step_tokens > 0, "no decoder step has run");
   VLO_CUDA(cudaMemcpyAsync(d_hidden, e->xn, static_cast<size_t>(e->last_step_tokens) * e->cfg.hidden_size * sizeof(bf16),
                            cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(cuda_stream)));
@@ -932,6 +1070,7 @@ int vlo_last_step_hidden(vlo_engine* e, void* d_hidden, void* cuda_stream) {
 }
 
 int vlo_last_step_logits(vlo_engine* e, void* d_logits, void* cuda_stream) {
+  DevGuard dev_guard(e);
   VLO_CHECK(e != nullptr && e->last_step_tokens > 0, "no decoder step has run");
   const vlo_config& c = e->cfg;
   return gemm_ws_store16(FMT_BF16, e->lm_head, c.vocab_size, e->xn, e->last_step_tokens, c.hidden_size, d_logits,

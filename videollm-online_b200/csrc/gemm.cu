@@ -3,6 +3,7 @@
 // selection and kernel dispatch.
 #include "gemm.cuh"
 #include "gemm_ws.cuh"
+#include "gemm_wsf.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -109,9 +110,11 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& arg
 
 // Query tensor [n_tok][n_heads][128] bf16 as a 3-D map; one box = (64 dims, G heads of one kv head, 128/G tokens)
 // lands in shared memory as 128 rows of 128 B ordered row = token * G + head: the K-major SW128 A tile of the
-// attention kernel.  Tokens past n_tok are zero-filled by the TMA unit.
-int tmap_q3d_sw128(const void* ptr, int n_tok, int n_heads, int G, CUtensorMap* out) {
-  TmapKey key{ptr, n_tok, n_heads, -G, 3};
+// attention kernel.  Tokens past n_tok are zero-filled by the TMA unit.  box_rows (32 / 64 / 128, a multiple of G)
+// selects a smaller box of box_rows / G tokens: the v3 kernel stacks 128 / box_rows copies of it (key slicing).
+int tmap_q3d_sw128(const void* ptr, int n_tok, int n_heads, int G, CUtensorMap* out, int box_rows) {
+  if (box_rows <= 0) box_rows = 128;
+  TmapKey key{ptr, n_tok, n_heads, -G, 3 + 16 * box_rows};
   {
     std::lock_guard<std::mutex> g(g_tmap_mu);
     auto it = g_tmaps.find(key);
@@ -124,9 +127,10 @@ int tmap_q3d_sw128(const void* ptr, int n_tok, int n_heads, int G, CUtensorMap* 
   if (enc == nullptr) return fail("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail("TMA operand not 16-byte aligned");
   if (G < 1 || 128 % G != 0 || n_heads % G != 0) return fail("tmap_q3d: GQA group must divide 128 and n_heads");
+  if (box_rows % G != 0 || box_rows > 128) return fail("tmap_q3d: box rows must be a multiple of the GQA group, <= 128");
   cuuint64_t dims[3] = {128, static_cast<cuuint64_t>(n_heads), static_cast<cuuint64_t>(n_tok)};
   cuuint64_t strides[2] = {256, static_cast<cuuint64_t>(n_heads) * 256};
-  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(G), static_cast<cuuint32_t>(128 / G)};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(G), static_cast<cuuint32_t>(box_rows / G)};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -328,6 +332,45 @@ int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream) {
   VLO_WS_CASE(FMT_F16, 192)
 #undef VLO_WS_CASE
   return fail("gemm_ws_launch: no kernel instance");
+}
+
+// ------------------------------------------------------------------------------------------------
+// stream-K GEMM with the fused finisher epilogue (gemm_wsf.cuh)
+namespace {
+template <int BN, int STAGES, int EPI>
+int launch_wsf(const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsfArgs& a, cudaStream_t stream) {
+  auto kern = gemm_wsf_kernel<BN, STAGES, EPI>;
+  using Cfg = GemmWsfCfg<BN, STAGES>;
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes)) return -1;
+  if (prof_on())
+    prof_begin(PROF_GEMM_STREAM, stream, 2.0 * a.k * (static_cast<double>(a.rows_w) + a.rows_x) + 2.0 * a.rows_x * a.rows_w);
+  VLO_CUDA(launch_pdl(kern, dim3(a.sk.G), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tw, tx, a));
+  prof_end(stream);
+  count_launch();
+  return 0;
+}
+template <int BN, int STAGES>
+int launch_wsf_epi(int epi, const CUtensorMap& tw, const CUtensorMap& tx, const GemmWsfArgs& a, cudaStream_t stream) {
+  if (epi == WSF_RESID) return launch_wsf<BN, STAGES, WSF_RESID>(tw, tx, a, stream);
+  if (epi == WSF_QKV) return launch_wsf<BN, STAGES, WSF_QKV>(tw, tx, a, stream);
+  if (epi == WSF_SWIGLU) return launch_wsf<BN, STAGES, WSF_SWIGLU>(tw, tx, a, stream);
+  return fail("gemm_wsf_launch: unknown epilogue");
+}
+}  // namespace
+
+int gemm_wsf_launch(const GemmWsfArgs& a, const void* w, const void* x, int epi, cudaStream_t stream) {
+  VLO_CHECK(a.k > 0 && a.k % kGemmBK == 0, "K must be a positive multiple of 64");
+  VLO_CHECK(a.rows_w > 0 && a.rows_x > 0 && a.rows_x <= 128, "gemm_wsf: 1..128 token rows");
+  VLO_CHECK(epi == WSF_RESID || a.rows_w % kGemmBM == 0, "gemm_wsf: QKV / SwiGLU epilogues need whole 128-row tiles");
+  const int bn = a.rows_x <= 16 ? 16 : (a.rows_x <= 32 ? 32 : (a.rows_x <= 64 ? 64 : 128));
+  VLO_CHECK(a.sk.U == static_cast<long long>((a.rows_w + kGemmBM - 1) / kGemmBM) * (a.k / kGemmBK), "gemm_wsf: plan mismatch");
+  CUtensorMap tw, tx;
+  if (get_tmap(w, a.rows_w, a.k, kGemmBM, FMT_BF16, &tw) != 0) return -1;
+  if (get_tmap(x, a.rows_x, a.k, bn, FMT_BF16, &tx) != 0) return -1;
+  if (bn == 16) return launch_wsf_epi<16, 6>(epi, tw, tx, a, stream);   // 6 x 18 KB: shares an SM with a ViT CTA (gemm_ws)
+  if (bn == 32) return launch_wsf_epi<32, ws_default_stages(32)>(epi, tw, tx, a, stream);
+  if (bn == 64) return launch_wsf_epi<64, ws_default_stages(64)>(epi, tw, tx, a, stream);
+  return launch_wsf_epi<128, ws_default_stages(128)>(epi, tw, tx, a, stream);
 }
 
 }  // namespace vlo

@@ -45,10 +45,37 @@ def engine_weight_spec(cfg: LiveConfig, max_positions: int) -> Dict[str, tuple]:
     return s
 
 
+def _flat_layout(spec: Dict[str, tuple], n_buckets: int):
+    """Deal the tensors (sorted by name) into <= n_buckets contiguous byte ranges of similar size.
+    Returns [(bucket_bytes, [(name, offset, shape, dtype)])]; offsets are 256-byte aligned (TMA / 16-byte vector loads)."""
+    items = []
+    for name in sorted(spec):
+        shape, dtype = spec[name]
+        n = 1
+        for d in shape:
+            n *= d
+        items.append((name, shape, dtype, n * torch.empty(0, dtype=dtype).element_size()))
+    total = sum(-(-b // 256) * 256 for *_, b in items)
+    target = -(-total // max(1, n_buckets))
+    buckets, cur, off = [], [], 0
+    for name, shape, dtype, nbytes in items:
+        cur.append((name, off, shape, dtype))
+        off += -(-nbytes // 256) * 256
+        if off >= target and len(buckets) < n_buckets - 1:
+            buckets.append((off, cur))
+            cur, off = [], 0
+    if cur:
+        buckets.append((off, cur))
+    return buckets
+
+
 def broadcast_weights(cfg: LiveConfig, weights: Optional[Dict[str, torch.Tensor]], device, max_positions: int,
-                      dist=None, src: int = 0) -> Dict[str, torch.Tensor]:
-    """Rank `src` passes its engine-layout dict, the others pass None; everyone returns the full dict on
-    `device`.  Tensors go out in fixed (sorted) order, one NCCL broadcast each (biggest: lm_head, 1 GB)."""
+                      dist=None, src: int = 0, n_buckets: int = 8, release_source: bool = False) -> Dict[str, torch.Tensor]:
+    """Rank `src` passes its engine-layout dict, the others pass None; everyone returns the full dict on `device`.
+    The ~560 tensors (16.7 GB) travel as <= `n_buckets` flat byte buffers, one NCCL broadcast each over NVLink/NVSwitch
+    (per-tensor broadcasts cost 1.2 s at 8 GPUs: launch latency, not bandwidth); the returned tensors are views into
+    those buffers (256-byte aligned), on the source rank too, so every rank ends with the same memory layout.
+    release_source=True empties the source dict entry by entry while packing."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         if weights is None:
             raise ValueError("single process: weights must be provided")
@@ -60,14 +87,24 @@ def broadcast_weights(cfg: LiveConfig, weights: Optional[Dict[str, torch.Tensor]
         missing = set(spec) - set(weights)
         if missing:
             raise KeyError(f"source rank lacks tensors: {sorted(missing)[:5]}")
-    for name in sorted(spec):
-        shape, dtype = spec[name]
-        if is_src:
-            t = weights[name].to(device).contiguous()
-            if tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-                raise ValueError(f"{name}: {tuple(t.shape)}/{t.dtype} does not match spec {shape}/{dtype}")
-        else:
-            t = torch.empty(shape, dtype=dtype, device=device)
-        dist.broadcast(t, src=src)
-        out[name] = t
+    for nbytes, members in _flat_layout(spec, n_buckets):
+        flat = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        views = []
+        for name, off, shape, dtype in members:
+            n = 1
+            for d in shape:
+                n *= d
+            esz = torch.empty(0, dtype=dtype).element_size()
+            v = flat[off:off + n * esz].view(dtype).view(*shape)
+            if is_src:
+                t = weights[name]
+                if tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                    raise ValueError(f"{name}: {tuple(t.shape)}/{t.dtype} does not match spec {shape}/{dtype}")
+                v.copy_(t.to(device), non_blocking=True)
+                if release_source:
+                    weights[name] = None      # drop the source copy as soon as it is packed (16.7 GB at full size)
+            views.append((name, v))
+        dist.broadcast(flat, src=src)
+        for name, v in views:
+            out[name] = v
     return out

@@ -133,6 +133,9 @@ class Engine:
     def kv_truncate(self, sid: int, new_len: int):
         check(self.lib.vlo_kv_truncate(self._h, sid, new_len), "vlo_kv_truncate")
 
+    def kv_copy_prefix(self, src_sid: int, dst_sid: int, n_tokens: int):
+        check(self.lib.vlo_kv_copy_prefix(self._h, src_sid, dst_sid, n_tokens, self._stream()), "vlo_kv_copy_prefix")
+
     def kv_fill_synthetic(self, sid: int, n_tokens: int, seed: int = 0):
         check(self.lib.vlo_kv_fill_synthetic(self._h, sid, n_tokens, seed, self._stream()), "vlo_kv_fill_synthetic")
 
@@ -152,7 +155,8 @@ class Engine:
         """uint8 [B,3,S,S] -> bf16 [B*frame_num_tokens, hidden] (visual_embed, models/modeling_live.py:21-27)."""
         if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4:
             raise VloError("vit_encode expects uint8 frames [B,3,S,S]")
-        frames_u8 = frames_u8.to(self.device).contiguous()
+        # pinned host frames (a live feed) are copied asynchronously on the caller's stream
+        frames_u8 = frames_u8.to(self.device, non_blocking=frames_u8.device.type == "cpu" and frames_u8.is_pinned()).contiguous()
         B = frames_u8.shape[0]
         S = self.cfg.frame_resolution
         if tuple(frames_u8.shape[1:]) != (3, S, S):

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import collections
 import logging
+import threading
 from dataclasses import asdict
 
 import torch
@@ -62,10 +63,33 @@ class LiveInfer:
         # decoder works on the current one (same per-frame arithmetic; a live stream delivers the next frame
         # during the current step anyway).  Set prefetch_next = False for strictly sequential behaviour.
         self.prefetch_next = True
+        # frames encoded per encode-ahead call: with a loaded clip the next `prefetch_depth` frames go through ONE batched
+        # ViT pass (the reference itself batches every frame between two input_video_stream calls, demo/inference.py:106);
+        # a batch of 4 amortises the ViT's weight stream and launch chain over 4 frames.
+        self.prefetch_depth = 4
         self._side = torch.cuda.Stream(self.device)
-        self._prefetched = None   # (frame_idx, embeds tensor, event)
-        self._want_prefetch = None  # frame index to encode ahead right after the next decoder step is enqueued
+        # demo/app.py drives input_video_stream and __call__ from separate Gradio callbacks: both touch the
+        # engine's single set of ViT workspaces and the encode-ahead state, so their bodies are serialised.
+        self._lock = threading.RLock()
+        self._alloc_step_buffers(256)
+        self._row_ids_cache = {}
+        self._prefetched = {}       # frame_idx -> (embeds [frame_num_tokens, hidden], event)
+        self._prefetch_event = None   # last event recorded on the side stream (it owns the engine's ViT workspaces)
+        self._want_prefetch = None  # first frame index to encode ahead right after the next decoder step is enqueued
         self.reset()
+
+    def _alloc_step_buffers(self, rows: int):
+        self._packed = torch.zeros(rows, self.hidden_size, dtype=torch.bfloat16, device=self.device)
+        self._row_ids_host = torch.zeros(rows, dtype=torch.int64).pin_memory()
+        self._row_ids_dev = torch.zeros(rows, dtype=torch.int64, device=self.device)
+
+    def _drop_prefetch(self):
+        """Forget encoded-ahead frames; an encode-ahead still in flight owns the ViT workspaces: order behind it."""
+        if getattr(self, "_prefetch_event", None) is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._prefetch_event)
+        self._prefetched = {}
+        self._prefetch_event = None
+        self._want_prefetch = None
 
     # ------------------------------------------------------------------ session control
     def reset(self):
@@ -77,19 +101,24 @@ class LiveInfer:
         self.last_ids = torch.tensor([[]], dtype=torch.long)
         self._kv.engine.stream_reset(self._kv.stream_id)
         self.past_key_values = None
-        if getattr(self, "_prefetched", None) is not None:   # an encode-ahead in flight owns the ViT workspaces
-            torch.cuda.current_stream(self.device).wait_event(self._prefetched[2])
-        self._prefetched = None
-        self._want_prefetch = None
+        self._drop_prefetch()
 
-    def load_video(self, video_path_or_tensor):
+    def load_video(self, video_path_or_tensor, keep_on_host: bool = False):
         """Reference: read_video(...)[0].to('cuda') (demo/inference.py:111-115).  Accepts a uint8
-        [T,3,H,W] tensor directly (synthetic clips) or a path decodable by torchvision/cv2."""
+        [T,3,H,W] tensor directly (synthetic clips) or a path decodable by torchvision/cv2.
+        keep_on_host=True leaves the clip in pinned host memory (a live feed): every frame is then copied to the GPU
+        asynchronously by the step that encodes it instead of the whole clip being resident."""
         if isinstance(video_path_or_tensor, torch.Tensor):
             vt = video_path_or_tensor
         else:
             vt = _read_video_tchw(video_path_or_tensor, fps=self.frame_fps, resolution=self.frame_resolution)
-        self.video_tensor = vt.to(self.device)
+        with self._lock:
+            # an encode-ahead of the previous clip must neither be consumed nor keep reading the old tensor
+            self._drop_prefetch()
+            if keep_on_host:
+                self.video_tensor = vt if (vt.device.type == "cpu" and vt.is_pinned()) else vt.cpu().pin_memory()
+            else:
+                self.video_tensor = vt.to(self.device)
         self.num_video_frames = self.video_tensor.size(0)
         self.video_duration = self.video_tensor.size(0) / self.frame_fps
         logger.warning(f'{"tensor" if isinstance(video_path_or_tensor, torch.Tensor) else video_path_or_tensor} -> '
@@ -102,25 +131,36 @@ class LiveInfer:
         return f'(NOTE: Received "{query}" (at {self.video_time}s). Please wait until previous frames have been processed)'
 
     def input_video_stream(self, video_time):
+        with self._lock:
+            self._input_video_stream(video_time)
+
+    def _input_video_stream(self, video_time):
         frame_idx = int(video_time * self.frame_fps)
         if frame_idx > self.last_frame_idx:
             ranger = range(self.last_frame_idx + 1, frame_idx + 1)
-            start, embeds = ranger.start, []
             main = torch.cuda.current_stream(self.device)
-            if self._prefetched is not None and self._prefetched[0] == start:
-                _, pe, ev = self._prefetched
-                main.wait_event(ev)
-                pe.record_stream(main)
-                embeds.append(pe)
-                start += 1
-            elif self._prefetched is not None:
-                main.wait_event(self._prefetched[2])   # a stale encode-ahead still owns the engine's ViT workspaces
-            self._prefetched = None
-            if start < ranger.stop:
-                embeds.extend(self.model.visual_embed(self.video_tensor[start:ranger.stop]).split(self.frame_num_tokens))
+            embeds, r = [], ranger.start
+            while r < ranger.stop:
+                hit = self._prefetched.pop(r, None)
+                if hit is not None:                     # encoded ahead on the side stream
+                    pe, ev = hit
+                    main.wait_event(ev)
+                    pe.record_stream(main)
+                    embeds.append(pe)
+                    r += 1
+                    continue
+                r2 = r                                  # contiguous run of frames that were not encoded ahead
+                while r2 < ranger.stop and r2 not in self._prefetched:
+                    r2 += 1
+                if self._prefetch_event is not None:    # a side-stream ViT may still own the engine's ViT workspaces
+                    main.wait_event(self._prefetch_event)
+                embeds.extend(self.model.visual_embed(self.video_tensor[r:r2]).split(self.frame_num_tokens))
+                r = r2
+            for k in [k for k in self._prefetched if k <= frame_idx]:   # skipped-over frames
+                del self._prefetched[k]
             self.frame_embeds_queue.extend([(r / self.frame_fps, e) for r, e in zip(ranger, embeds)])
             nxt = frame_idx + 1
-            self._want_prefetch = nxt if (self.prefetch_next and self.video_tensor is not None
+            self._want_prefetch = nxt if (self.prefetch_next and self.video_tensor is not None and nxt not in self._prefetched
                                           and nxt < self.video_tensor.size(0)) else None
         self.last_frame_idx = frame_idx
         self.video_time = video_time
@@ -128,31 +168,54 @@ class LiveInfer:
     # ------------------------------------------------------------------ decoder steps
     def _forward(self, ids: torch.Tensor, frame_embeds: torch.Tensor = None):
         """One KV-append step over [embed(ids) ; frame_embeds]; returns the device decision (host copy)."""
+        with self._lock:
+            return self._forward_locked(ids, frame_embeds)
+
+    def _forward_locked(self, ids: torch.Tensor, frame_embeds: torch.Tensor = None):
         eng = self.model.engine
-        ids = ids.reshape(-1).to(torch.int64)
-        n_ids = ids.numel()
+        id_list = [int(x) for x in ids.reshape(-1).tolist()]
+        n_ids = len(id_list)
         n_fr = 0 if frame_embeds is None else frame_embeds.shape[0]
-        packed = torch.empty(n_ids + n_fr, self.hidden_size, dtype=torch.bfloat16, device=self.device)
+        T = n_ids + n_fr
+        # pre-allocated step buffers: no per-step torch.empty / torch.cat / pageable H2D on the hot path
+        if T > self._packed.shape[0]:
+            self._alloc_step_buffers(2 * T)
+        packed = self._packed[:T]
         if n_fr:
             packed[n_ids:] = frame_embeds.view(-1, self.hidden_size)
-        row_ids = torch.cat([ids, torch.full((n_fr,), -1, dtype=torch.int64)]).to(self.device, non_blocking=True)
+        key = (tuple(id_list), n_fr)
+        row_ids = self._row_ids_cache.get(key) if n_fr else None   # steady state: [interval id | 10 frame rows]
+        if row_ids is None:
+            host = self._row_ids_host[:T]
+            host[:n_ids] = torch.tensor(id_list, dtype=torch.int64)
+            host[n_ids:] = -1
+            if n_fr:    # frame steps repeat (same prefix ids): keep their device copy
+                row_ids = host.to(self.device, non_blocking=True)
+                if len(self._row_ids_cache) < 64:
+                    self._row_ids_cache[key] = row_ids
+            else:       # prompts / AR tokens: one pinned -> device copy, consumed before the decision read-back below
+                row_ids = self._row_ids_dev[:T]
+                row_ids.copy_(host, non_blocking=True)
         main = torch.cuda.current_stream(self.device)
         pre = None
         if self._want_prefetch is not None:
             pre = torch.cuda.Event()
             pre.record(main)
-        eng.step([self._kv.stream_id], [n_ids + n_fr], packed, row_ids=row_ids)   # token rows gathered on the device
+        eng.step([self._kv.stream_id], [T], packed, row_ids=row_ids)   # token rows gathered on the device
         self.past_key_values = self._kv
         if pre is not None:
             # encode-ahead of the next frame, enqueued AFTER the step's launches (the host is the critical path right
             # after a decision read-back) but ordered only behind what preceded the step: it runs concurrently with it
             nxt, self._want_prefetch = self._want_prefetch, None
+            stop = min(nxt + max(1, int(self.prefetch_depth)), self.video_tensor.size(0))
             self._side.wait_event(pre)
             with torch.cuda.stream(self._side):
-                pe = self.model.visual_embed(self.video_tensor[nxt:nxt + 1])
+                pe = self.model.visual_embed(self.video_tensor[nxt:stop]).split(self.frame_num_tokens)
                 ev = torch.cuda.Event()
                 ev.record(self._side)
-            self._prefetched = (nxt, pe, ev)
+            for k, e in zip(range(nxt, stop), pe):
+                self._prefetched[k] = (e, ev)
+            self._prefetch_event = ev
         dec = eng.read_decisions(1)[0]
         if self.decision_hook is not None:
             dec = self.decision_hook(dec, self._n_calls)

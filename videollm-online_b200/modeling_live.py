@@ -126,6 +126,117 @@ class LiveLlamaForCausalLM:
     def new_stream(self) -> StreamKV:
         return StreamKV(self.engine, self.engine.stream_open())
 
+    # --- evaluation
+    def forward_all_logits(self, inputs_embeds: torch.Tensor, past_key_values: StreamKV) -> torch.Tensor:
+        """Teacher-forced KV-append forward returning the logits of EVERY position ([L, V] bf16), fed in chunks of
+        the engine's step capacity (chunked streaming == one causal pass): the reference's
+        `self.forward(..., use_cache=True).logits[0]` (models/modeling_live.py:67) on the engine's cache."""
+        eng = self.engine
+        x = inputs_embeds.reshape(-1, self.config.hidden_size).to(torch.bfloat16)
+        outs = []
+        for lo in range(0, x.shape[0], eng.max_step_tokens):
+            chunk = x[lo:lo + eng.max_step_tokens].contiguous()
+            eng.step([past_key_values.stream_id], [chunk.shape[0]], chunk, want_logits=False)
+            outs.append(eng.last_step_logits(chunk.shape[0]))
+        return torch.cat(outs, 0)
+
+    @torch.no_grad()
+    def stream_evaluate(self, input_ids: torch.LongTensor, labels: torch.LongTensor, frames: torch.Tensor,
+                        ignore_token_id: int = -100, frame_token_interval_threshold: float = 0.0, **kwargs):
+        """models/modeling_live.py:44-168 on the engine: same metrics, same order of operations.  The full forward runs
+        through `forward_all_logits`; the look-ahead of a turn whose frames were all judged "silent" (:110-141) runs on
+        a scratch stream holding a copy of the first `stop` cache positions (`vlo_kv_copy_prefix`, the engine's
+        trim_past_key_values(pkv, 0, stop)), so the evaluated conversation's own cache survives.
+        Returns tensor([lm_ppl, frame_diff, fluency, lm_correctness]) on the engine's device."""
+        assert input_ids.size(0) == labels.size(0) == 1
+        eng, cfg, dev = self.engine, self.config, self.engine.device
+        input_id, label = input_ids[0].to(dev), labels[0].to(dev)
+        frames = frames.to(dev)
+        zero = torch.tensor(0, dtype=torch.int, device=dev)
+        one = torch.tensor(1, dtype=torch.int, device=dev)
+        turn_stops = ((input_id == cfg.eos_token_id).nonzero() + 1)[:, 0].tolist()
+        turn_starts = [0] + turn_stops[:-1]
+        num_turns = len(turn_starts)
+        kv, scratch = self.new_stream(), None
+        try:
+            logit = self.forward_all_logits(self.joint_embed(input_id[None], frames)[0], kv)
+            v_id = cfg.v_placeholder_id
+            use_interval = cfg.frame_token_interval_id is not None
+            interval_id = cfg.frame_token_interval_id if use_interval else cfg.eos_token_id
+            fnt = int(cfg.frame_token_cls) + (cfg.frame_token_pooled[0] * cfg.frame_token_pooled[1] if cfg.frame_token_pooled else 0)
+            past_num_frames = 0
+            lm_ppls, frame_diffs, fluencies, lm_correctness = [], [], [], []
+            for r, (turn_start, turn_stop) in enumerate(zip(turn_starts, turn_stops)):
+                turn_label = label[turn_start:turn_stop]
+                turn_learn_mask = turn_label != ignore_token_id
+                if not turn_learn_mask.any():
+                    continue
+                turn_logit = logit[turn_start:turn_stop]
+                turn_input_id = input_id[turn_start:turn_stop]
+                turn_v_mask = turn_input_id == v_id
+                turn_num_frames = turn_v_mask.sum() // fnt
+                turn_stream_mask = turn_v_mask & turn_learn_mask
+                turn_lm_mask = turn_learn_mask & ~turn_stream_mask
+                if turn_lm_mask.any():
+                    ml, mt = turn_logit[turn_lm_mask], turn_label[turn_lm_mask]
+                    lm_ppls.append(torch.nn.functional.cross_entropy(ml, mt).exp())
+                    wrong = ml.argmax(dim=-1) != mt
+                    num_lm_correct_tokens = wrong.nonzero()[0, 0] if wrong.any() else (~wrong).sum()
+                    lm_correctness.append(num_lm_correct_tokens / mt.numel())
+                if turn_stream_mask.any():
+                    score = turn_logit.softmax(dim=-1)[turn_stream_mask]
+                    if frame_token_interval_threshold > 0:
+                        score[score[:, interval_id] < frame_token_interval_threshold] = 0
+                    pred = score.argmax(dim=-1) != interval_id
+                    if pred.any():
+                        frame_diff = turn_stream_mask.sum() - pred.nonzero()[0, 0] - 1
+                    else:
+                        last_stream_idx = turn_stream_mask.nonzero()[-1, 0]
+                        if r == num_turns - 1:
+                            frame_diff = zero
+                        else:
+                            next_nf = (input_id[turn_starts[r + 1]:turn_stops[r + 1]] == v_id).sum() // fnt
+                            n_app = min(next_nf, turn_num_frames - 1)
+                            if n_app == 0:
+                                frame_diff = zero
+                            else:
+                                a0 = int(past_num_frames + turn_num_frames)
+                                app_frames = frames[a0:a0 + int(n_app)]
+                                ph = ([interval_id] if use_interval else []) + [v_id] * fnt
+                                app_ids = torch.tensor(ph * int(n_app), dtype=torch.long, device=dev)
+                                if scratch is None:
+                                    scratch = self.new_stream()
+                                eng.kv_copy_prefix(kv.stream_id, scratch.stream_id, int(turn_start + last_stream_idx + 1))
+                                app_logit = self.forward_all_logits(self.joint_embed(app_ids[None], app_frames)[0], scratch)
+                                idxs = torch.arange(len(ph) - 1, len(app_ids), len(ph), device=dev)
+                                app_score = app_logit[idxs].softmax(dim=-1)
+                                if frame_token_interval_threshold > 0:
+                                    app_score[app_score[:, interval_id] < frame_token_interval_threshold] = 0
+                                app_pred = app_score.argmax(dim=-1) != interval_id
+                                frame_diff = -(app_pred.nonzero()[0, 0] + 1) if app_pred.any() else -n_app
+                    frame_diffs.append(torch.as_tensor(frame_diff, device=dev).abs())
+                if turn_lm_mask.any() and turn_stream_mask.any():
+                    n_v = turn_stream_mask.sum()
+                    n_valid = mt.numel() + n_v
+                    if frame_diff == 0:
+                        fluency = (n_v + num_lm_correct_tokens) / n_valid
+                    elif frame_diff > 0:
+                        fluency = (n_v - frame_diff) / n_valid
+                    else:
+                        fluency = (n_v - 1) / n_valid
+                    fluencies.append(fluency)
+                past_num_frames += turn_num_frames
+        finally:
+            eng.stream_close(kv.stream_id)
+            if scratch is not None:
+                eng.stream_close(scratch.stream_id)
+        f32 = lambda t: torch.as_tensor(t, device=dev).float()
+        lm_ppl = torch.stack(lm_ppls).mean() if lm_ppls else one
+        frame_diff = torch.stack(frame_diffs).float().mean() if frame_diffs else zero
+        fluency = torch.stack([f32(x) for x in fluencies]).mean() if fluencies else one
+        lm_c = torch.stack([f32(x) for x in lm_correctness]).mean() if lm_correctness else one
+        return torch.stack([f32(lm_ppl), f32(frame_diff), f32(fluency), f32(lm_c)])
+
     def __call__(self, input_ids: torch.Tensor = None, frames: torch.Tensor = None, inputs_embeds: torch.Tensor = None,
                  past_key_values: Optional[StreamKV] = None, use_cache: bool = True, return_dict: bool = True, **_):
         """KV-append forward (models/live_llama/modeling_live_llama.py:24-67), batch 1."""

@@ -129,13 +129,15 @@ class ByteTokenizer:
 
 
 def build_live_tokenizer_and_update_config(llm_pretrained: str, model_config: LiveConfig):
-    """models/tokenization_live.py:110-122.  Uses the HF tokenizer when `llm_pretrained` resolves
-    locally; otherwise the byte tokenizer (ids then come from the config, never hard-coded)."""
-    try:
-        from transformers import AutoTokenizer
-        tok = AutoTokenizer.from_pretrained(llm_pretrained, use_fast=True, padding_side="left", local_files_only=True)
-    except Exception:
+    """models/tokenization_live.py:110-122.  Uses the HF tokenizer when `llm_pretrained` names a local checkpoint
+    directory.  The byte tokenizer (ids then come from the config, never hard-coded) is used ONLY when no checkpoint is
+    named (synthetic weights): with real weights a missing / unreadable tokenizer must fail loudly, as the reference
+    does, instead of feeding byte ids to a trained embedding table."""
+    import os
+    if not llm_pretrained or not os.path.isdir(llm_pretrained):
         return ByteTokenizer(model_config)
+    from transformers import AutoTokenizer
+    tok = AutoTokenizer.from_pretrained(llm_pretrained, use_fast=True, padding_side="left", local_files_only=True)
     tok.add_special_tokens({"additional_special_tokens": [model_config.v_placeholder]})
     model_config.v_placeholder_id = len(tok) - 1
     model_config.frame_token_interval_id = (tok.convert_tokens_to_ids(model_config.frame_token_interval)

@@ -10,7 +10,8 @@ same dict feeds the oracle, the HF reference modules (golden generation) and —
 Engine layout (name -> tensor), all contiguous on the engine's device:
   embed [V,H] bf16 | final_norm [H] bf16 | lm_head [V,H] bf16 | rope.cos / rope.sin [max_pos,64] bf16
   L{i}.in_norm, L{i}.post_norm [H] bf16 | L{i}.qkv [(nh+2nkv)*128, H] bf16 (q|k|v rows)
-  L{i}.o [H, nh*128] | L{i}.gate_up [2I, H] (gate rows then up rows) | L{i}.down [H, I]   (bf16)
+  L{i}.o [H, nh*128] | L{i}.gate_up [2I, H] (tile-interleaved: 64 gate rows of features 64j.., then the matching 64 up
+  rows, per 128-row tile j - one MMA tile then holds both operands of SwiGLU) | L{i}.down [H, I]   (bf16)
   conn.0.w [H,C] bf16, conn.0.b [H] f32, conn.2.w [H,H] bf16, conn.2.b [H] f32
   vit.patch.w [C, 3*ps*ps] f16, vit.patch.b [C] f32, vit.pos [P,C] f32, vit.post_ln.{w,b} f32
   vit.L{i}.{ln1,ln2}.{w,b} f32, vit.L{i}.qkv.w [3C,C] f16 (+ .b f32), out.w [C,C], fc1.w [M,C], fc2.w [C,M]
@@ -152,6 +153,14 @@ def _b32_from16(t: torch.Tensor, dt16) -> torch.Tensor:
     return t.to(dt16).to(torch.float32).contiguous()
 
 
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """[I, H] + [I, H] -> [2I, H] with rows ordered per 128-row tile: gate[64j:64j+64] then up[64j:64j+64]."""
+    I, H = gate.shape
+    if I % 64 != 0:
+        raise ValueError("intermediate_size must be a multiple of 64")
+    return torch.stack([gate.view(I // 64, 64, H), up.view(I // 64, 64, H)], 1).reshape(2 * I, H).contiguous()
+
+
 def pack_llm_for_engine(cfg: LiveConfig, sd: StateDict, device, max_positions: int) -> StateDict:
     bf = torch.bfloat16
     out: StateDict = {}
@@ -171,7 +180,7 @@ def pack_llm_for_engine(cfg: LiveConfig, sd: StateDict, device, max_positions: i
         out[f"L{i}.qkv"] = torch.cat([take(p + "self_attn.q_proj.weight"), take(p + "self_attn.k_proj.weight"),
                                       take(p + "self_attn.v_proj.weight")], 0).contiguous()
         out[f"L{i}.o"] = take(p + "self_attn.o_proj.weight")
-        out[f"L{i}.gate_up"] = torch.cat([take(p + "mlp.gate_proj.weight"), take(p + "mlp.up_proj.weight")], 0).contiguous()
+        out[f"L{i}.gate_up"] = interleave_gate_up(take(p + "mlp.gate_proj.weight"), take(p + "mlp.up_proj.weight"))
         out[f"L{i}.down"] = take(p + "mlp.down_proj.weight")
     if "connector.0.weight" in sd:
         out["conn.0.w"] = take("connector.0.weight")
