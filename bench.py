@@ -388,7 +388,8 @@ def run_engine_arm(args):
         return dec
     li.decision_hook = _silent
     li.load_video(frames_host[:Wm + K + 1], keep_on_host=True)
-    li.past_key_values = li._kv                      # resume at the 10-minute position (cache pre-filled above)
+    eng.kv_fill_synthetic(sid, KV_START, seed=7 + rank)    # LiveInfer() reset the stream: back to the 10-minute position
+    li.past_key_values = li._kv
     li.last_ids = torch.tensor([[cfg.frame_token_interval_id]])
     for i in range(Wm):
         li.input_video_stream(i / li.frame_fps)

@@ -277,8 +277,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         const float m_use = grow ? m_new : m_ref;
         const float alpha = (grow && m_ref != -INFINITY) ? exp2f((m_ref - m_new) * c) : 1.f;
         if (__any_sync(0xffffffffu, alpha != 1.f)) {
-          // O of this warp's 32 lanes must be rescaled: wait until PV_{j-1} has landed in TMEM
-          mbar_wait(o_done, (j - 1) & 1);
+          // O of this warp's 32 lanes must be rescaled: wait until PV_{j-1} has landed in TMEM (through its p_empty
+          // commit, which this thread follows phase by phase; a free-running per-PV barrier aliases, see attn_tc2.cuh)
+          mbar_wait(&p_empty[b ^ 1], ((j - 1) >> 1) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -320,7 +321,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__
         if (r == 0) VLO_TC_STAMP(2, 7 + 4 * j);
       }
       // ---- epilogue: partial (m, l, O) of this split; merged by attn_merge_kernel
-      mbar_wait(o_done, (nblk - 1) & 1);
+      mbar_wait(&p_empty[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);   // the last PV (see attn_tc2.cuh on parity aliasing)
       tc_fence_after();
       if (r == 0) VLO_TC_STAMP(2, 1);
       const int rows = it.q_count * G;

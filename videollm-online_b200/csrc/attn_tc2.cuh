@@ -53,7 +53,7 @@ struct AttnTc2Params {
 constexpr int kTc2CombStride = 132;   // floats per (slice, row) record in the combine buffer: O[128] | m | l | pad
 
 struct Tc2Ctx {
-  uint64_t *s_full, *s_empty, *p_full, *p_empty, *o_done;
+  uint64_t *s_full, *s_empty, *p_full, *p_empty;
   uint32_t tS, tO, tP;
   float* comb;            // shared-memory combine buffer (the K/V ring, free by then)
   int nblk, blk0, G, kvh, split;
@@ -137,8 +137,10 @@ __device__ __forceinline__ void tc2_softmax_role(const AttnTc2Params& pp, const 
     const float m_use = grow ? m_new : m_ref;
     const float alpha = (grow && m_ref != -INFINITY) ? exp2f((m_ref - m_new) * c) : 1.f;
     if (__any_sync(0xffffffffu, alpha != 1.f)) {
-      // O of this warp's 32 lanes must be rescaled: wait until PV_{j-1} has landed in TMEM
-      mbar_wait(cx.o_done, (j - 1) & 1);
+      // O of this warp's 32 lanes must be rescaled: wait until PV_{j-1} has landed in TMEM.  PV_i commits on
+      // p_empty[i & 1]; this thread has observed that barrier up to PV_{j-3} (its wait at block j-1), so the phase of
+      // PV_{j-1} is exactly one ahead: no parity aliasing (a free-running per-PV barrier would alias, see epilogue).
+      mbar_wait(&cx.p_empty[b ^ 1], ((j - 1) >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -191,8 +193,12 @@ __device__ __forceinline__ void tc2_softmax_role(const AttnTc2Params& pp, const 
     mbar_arrive(&cx.p_full[b]);
     if (L == 0) VLO_TC_STAMP(2, 7 + 4 * j);
   }
-  // ---- epilogue: partial (m, l, O) of this split; merged by attn_merge_kernel
-  mbar_wait(cx.o_done, (nblk - 1) & 1);
+  // ---- epilogue: partial (m, l, O) of this split; merged by attn_merge_kernel.
+  // Wait for the LAST PV through its p_empty commit: every softmax thread has followed p_empty[b] phase by phase (it
+  // waits for PV_{j-2} at block j), so PV_{nblk-1} is exactly the next phase.  A barrier that completes one phase per PV
+  // and is only looked at here would alias: parity (nblk-1)&1 is also the parity of PV_{nblk-3}, and with the
+  // key-sliced softmax running ahead of the V stream the wait returned two PVs early.
+  mbar_wait(&cx.p_empty[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
   tc_fence_after();
   if (L == 0) VLO_TC_STAMP(2, 1);
   float w_self = 1.f;
@@ -300,8 +306,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   uint64_t* s_empty = s_full + 2;            // [2]   softmax has read S_j
   uint64_t* p_full = s_empty + 2;            // [2]   P_j in TMEM (and O rescaled)
   uint64_t* p_empty = p_full + 2;            // [2]   PV_j has consumed P buffer
-  uint64_t* o_done = p_empty + 2;            // [1]   PV_j complete (phase j)
-  uint64_t* q_ready = o_done + 1;            // [1]
+  uint64_t* q_ready = p_empty + 2;           // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -311,6 +316,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   const int split = code & 255, kvh = (code >> 8) & 255;
   const AttnItem it = p.items[code >> 16];
   if (threadIdx.x == 0) VLO_TC_STAMP(0, 0);
+  if (threadIdx.x == 0 && pp.dbg != nullptr) pp.dbg[static_cast<size_t>(blockIdx.x) * 192 + 60] = static_cast<long long>(globaltimer_ns());
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
@@ -329,7 +335,6 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       mbar_init(&p_full[i], 128);
       mbar_init(&p_empty[i], 1);
     }
-    mbar_init(o_done, 1);
     mbar_init(q_ready, 1);
     fence_mbar_init();
   }
@@ -429,7 +434,6 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
           }
           umma_commit(&v_empty[s]);
           umma_commit(&p_empty[b]);
-          umma_commit(o_done);
         };
         for (int j = 0; j < nblk; ++j) {
           const int s = j % NS;
@@ -455,7 +459,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     } else {
       // -------------------------------------------------------------- softmax / correction / epilogue warps
       Tc2Ctx cx;
-      cx.s_full = s_full, cx.s_empty = s_empty, cx.p_full = p_full, cx.p_empty = p_empty, cx.o_done = o_done;
+      cx.s_full = s_full, cx.s_empty = s_empty, cx.p_full = p_full, cx.p_empty = p_empty;
       cx.tS = tS, cx.tO = tO, cx.tP = tP;
       cx.comb = reinterpret_cast<float*>(kv_tile);
       cx.nblk = nblk, cx.blk0 = blk0, cx.G = G, cx.kvh = kvh, cx.split = split;
@@ -465,6 +469,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0 && pp.dbg != nullptr) {
+    pp.dbg[static_cast<size_t>(blockIdx.x) * 192 + 61] = static_cast<long long>(globaltimer_ns());
+    pp.dbg[static_cast<size_t>(blockIdx.x) * 192 + 62] = clock64();
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

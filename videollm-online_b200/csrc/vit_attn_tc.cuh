@@ -114,7 +114,6 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half* out, int 
           umma_f16_ts(tO, tP + static_cast<uint32_t>(pb * 64 + kk * 8), db, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&p_empty[pb]);
-        umma_commit(o_done);
       };
       for (int j = 0; j < nblk; ++j) {
         const int sb = j & 1;
@@ -185,7 +184,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half* out, int 
       const float m_use = grow ? m_new : m_ref;
       const float alpha = (grow && m_ref != -INFINITY) ? exp2f((m_ref - m_new) * c) : 1.f;
       if (__any_sync(0xffffffffu, alpha != 1.f)) {
-        mbar_wait(o_done, (j - 1) & 1);   // PV_{j-1} has landed: rescale O of this warp's 32 lanes
+        mbar_wait(&p_empty[sb ^ 1], ((j - 1) >> 1) & 1);   // PV_{j-1} has landed (phase-exact, see attn_tc2.cuh): rescale O
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -222,7 +221,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half* out, int 
       mbar_arrive(&p_full[sb]);
     }
     // ---- epilogue: out = O / l  (fp16)
-    mbar_wait(o_done, (nblk - 1) & 1);
+    mbar_wait(&p_empty[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);   // the last PV, phase-exact (see attn_tc2.cuh)
     tc_fence_after();
     if (warp_live) {   // warp-uniform: tcgen05.ld is .sync.aligned
       uint32_t v0[32], v1[32];
