@@ -367,7 +367,19 @@ int gemm_wsf_launch(const GemmWsfArgs& a, const void* w, const void* x, int epi,
   CUtensorMap tw, tx;
   if (get_tmap(w, a.rows_w, a.k, kGemmBM, FMT_BF16, &tw) != 0) return -1;
   if (get_tmap(x, a.rows_x, a.k, bn, FMT_BF16, &tx) != 0) return -1;
-  if (bn == 16) return launch_wsf_epi<16, 6>(epi, tw, tx, a, stream);   // 6 x 18 KB: shares an SM with a ViT CTA (gemm_ws)
+  if (bn == 16) {
+    // ring depth (VLO_WSF_STAGES=4|5|6).  6 x 18 KB + the 8.7 KB exchange tile = 118 KB: ONE such CTA per SM.  5 stages = 100 KB:
+    // the next GEMM of the chain becomes resident beside this one and fills its ring during this one's main loop and
+    // finisher tail.
+    static int st = 0;
+    if (st == 0) {
+      const char* e = getenv("VLO_WSF_STAGES");
+      st = e ? atoi(e) : 6;
+    }
+    if (st == 4) return launch_wsf_epi<16, 4>(epi, tw, tx, a, stream);
+    if (st == 5) return launch_wsf_epi<16, 5>(epi, tw, tx, a, stream);
+    return launch_wsf_epi<16, 6>(epi, tw, tx, a, stream);
+  }
   if (bn == 32) return launch_wsf_epi<32, ws_default_stages(32)>(epi, tw, tx, a, stream);
   if (bn == 64) return launch_wsf_epi<64, ws_default_stages(64)>(epi, tw, tx, a, stream);
   return launch_wsf_epi<128, ws_default_stages(128)>(epi, tw, tx, a, stream);
