@@ -168,6 +168,12 @@ int vlo_op_gemm(int fmt, int swap, int epi, int act, const void* d_a, int rows_a
 int vlo_op_gemm_ws(int fmt, int mode, const void* d_w, int rows_w, const void* d_x, int rows_x, int k, void* d_out,
                    int ld_out, long long plane_stride, const float* d_bias, int act, int n_ctas, int bn, int* h_max_planes,
                    void* cuda_stream);
+/* 2-CTA (tcgen05 cta_group::2) tensor-bound GEMM of the ViT trunk at batch >= 3 (csrc/gemm2.cuh), fp16:
+ *   epi 0: out16[rows_x][ld_out] = act(fp16(X W^T + bias));  epi 1: out32[rows_x][ld_out] += fp16(X W^T + bias)
+ *   (the fp32 residual stream).  bn = 256 | 128 features per CTA-pair tile; rows_w % 32 == 0; d_bias required.
+ * Replaces the cuBLAS GEMMs of HF:models/siglip/modeling_siglip.py:285-287, 309, 323-327. */
+int vlo_op_gemm2(const void* d_x, int rows_x, const void* d_w, int rows_w, int k, void* d_out, int ld_out, const float* d_bias,
+                 int act, int epi, int bn, void* cuda_stream);
 /* KV-append attention over one layer's cache (the graded kernel, K15):
  *   d_q bf16 [n_tok, n_heads, head_dim] (RoPE applied); d_k/d_v bf16 [n_kv_heads, kv_stride, head_dim];
  *   keys 0..kv_len-1 valid, the n_tok query tokens sit at positions kv_len-n_tok .. kv_len-1 (causal with

@@ -220,6 +220,11 @@ def test_checkpoint_directory_loader_roundtrip(tmp_path):
     assert set(got) == set(want)
     for k in want:
         assert torch.equal(got[k], want[k]), k
+    # adapter_config.json (written by PEFT next to the weights) overrides the CLI defaults for r / lora_alpha
+    import json
+    (ad_dir / "adapter_config.json").write_text(json.dumps({"r": r, "lora_alpha": alpha, "peft_type": "LORA"}))
+    got2 = _load_checkpoints(cfg, str(llm_dir), str(ad_dir), False, "cpu", 256, 999, 1.0)
+    assert torch.equal(got2["L0.qkv"], want["L0.qkv"]) and torch.equal(got2["lm_head"], want["lm_head"])
     # the adapter really changed the weights, and the connector came from the adapter
     assert not torch.equal(got["L0.qkv"], W.pack_llm_for_engine(cfg, full, "cpu", 256)["L0.qkv"])
     assert torch.equal(got["conn.0.w"], full["connector.0.weight"])

@@ -76,6 +76,7 @@ SIGNATURES = {
     "vlo_bench_gemm": (_I, [_P, _I, _I, C.POINTER(C.c_double), C.POINTER(_I), _P]),
     "vlo_op_gemm": (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I, _P, _P, _I, _I, _LL, _I, _P]),
     "vlo_op_gemm_ws": (_I, [_I, _I, _P, _I, _P, _I, _I, _P, _I, _LL, _P, _I, _I, _I, C.POINTER(_I), _P]),
+    "vlo_op_gemm2": (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
     "vlo_op_attn_version": (_I, [_I, _I]),
     "vlo_debug_attn_trace": (_I, [C.POINTER(_LL), _I]),
     "vlo_op_attn_ws_bytes": (C.c_int64, [_I, _I, _I, _I]),

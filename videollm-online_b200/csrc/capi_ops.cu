@@ -60,6 +60,23 @@ int vlo_op_gemm(int fmt, int swap, int epi, int act, const void* d_a, int rows_a
 
 extern "C" {
 
+int vlo_op_gemm2(const void* d_x, int rows_x, const void* d_w, int rows_w, int k, void* d_out, int ld_out, const float* d_bias,
+                 int act, int epi, int bn, void* cuda_stream) {
+  Gemm2Call c{};
+  c.x = d_x;
+  c.rows_x = rows_x;
+  c.w = d_w;
+  c.rows_w = rows_w;
+  c.k = k;
+  c.out = d_out;
+  c.ld_out = ld_out;
+  c.bias = d_bias;
+  c.act = act;
+  c.epi = epi;
+  c.bn = bn;
+  return gemm2_launch(c, static_cast<cudaStream_t>(cuda_stream));
+}
+
 int vlo_op_gemm_ws(int fmt, int mode, const void* d_w, int rows_w, const void* d_x, int rows_x, int k, void* d_out,
                    int ld_out, long long plane_stride, const float* d_bias, int act, int n_ctas, int bn, int* h_max_planes,
                    void* cuda_stream) {

@@ -123,6 +123,22 @@ struct GemmWsCall {
 int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_planes, int x_tiles = 1);
 int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream);
 
+// ---- 2-CTA (cta_group::2) tensor-bound GEMM for the ViT trunk (gemm2.cuh / gemm.cu): tokens on MMA-M, 256 x bn tiles per CTA pair
+struct Gemm2Call {
+  const void* x;      // [rows_x, k] fp16 activations
+  int rows_x;
+  const void* w;      // [rows_w, k] fp16 weights, rows_w a multiple of 32
+  int rows_w;
+  int k;
+  void* out;          // epi 0: fp16 [rows_x, ld_out] = act(fp16(acc + bias));  epi 1: fp32 [rows_x, ld_out] += fp16(acc + bias)
+  int ld_out;
+  const float* bias;
+  int act;
+  int epi;
+  int bn;             // 256 or 128 features per tile
+};
+int gemm2_launch(const Gemm2Call& c, cudaStream_t stream);
+
 // ---- stream-K GEMM with the fused finisher epilogue (gemm_wsf.cuh / gemm.cu); args struct defined in gemm_wsf.cuh
 struct GemmWsfArgs;
 int gemm_wsf_launch(const GemmWsfArgs& a, const void* w, const void* x, int epi, cudaStream_t stream);

@@ -743,9 +743,61 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
   VLO_CUDA(launch_pdl(layernorm_kernel<float>, dim3(rows), dim3(256), ln_smem, st, static_cast<const float*>(e->v_h),
                       e->vit[0].ln1_w, e->vit[0].ln1_b, e->v_xn, static_cast<float*>(nullptr), C, c.vit_ln_eps));
   count_launch();
+  // Batches of >= 3 frames (encode-ahead groups, multi-stream ticks, offline extraction) are tensor-bound: their trunk
+  // GEMMs run on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, gemm2.cuh) with tokens on MMA-M; out_proj / fc2 add
+  // straight into the fp32 residual stream and a plain LayerNorm kernel follows.  VLO_VIT_GEMM2=0: single-CTA path.
+  static int use_gemm2 = -1;
+  if (use_gemm2 < 0) {
+    const char* ev = getenv("VLO_VIT_GEMM2");
+    use_gemm2 = (ev != nullptr && ev[0] == '0') ? 0 : 1;
+  }
+  const bool pair_gemm = use_gemm2 && B >= 3 && C % 128 == 0 && M % 128 == 0;
+  auto gemm2 = [&](const __half* x, const __half* w, int n_out, int k, void* out, const float* bias, int act, int epi) -> int {
+    Gemm2Call g{};
+    g.x = x;
+    g.rows_x = rows;
+    g.w = w;
+    g.rows_w = n_out;
+    g.k = k;
+    g.out = out;
+    g.ld_out = n_out;
+    g.bias = bias;
+    g.act = act;
+    g.epi = epi;
+    // 256-wide tiles unless they leave most CTA pairs idle (the two C-wide GEMMs at small batch)
+    const int mt = (rows + 255) / 256;
+    g.bn = (n_out % 256 == 0 && mt * (n_out / 256) >= 60) ? 256 : 128;
+    return gemm2_launch(g, st);
+  };
+  auto plain_ln = [&](const float* lw, const float* lb, float* out32) -> int {
+    VLO_CUDA(launch_pdl(layernorm_kernel<float>, dim3(rows), dim3(256), ln_smem, st, static_cast<const float*>(e->v_h), lw, lb,
+                        e->v_xn, out32, C, c.vit_ln_eps));
+    count_launch();
+    return 0;
+  };
   for (int l = 0; l < c.vit_layers; ++l) {
     const VitLayer& v = e->vit[l];
     SkCall sc{};
+    if (pair_gemm) {
+      if (gemm2(e->v_xn, v.qkv_w, 3 * C, C, e->v_qkv, v.qkv_b, ACT_NONE, 0)) return -1;
+      prof_begin(PROF_VIT_ATTN, st, 4.0 * rows * C * 2);
+      if (attn_tc)
+        VLO_CUDA(launch_pdl(vit_attn_tc_kernel, dim3((P + kVitTcBlk - 1) / kVitTcBlk, c.vit_heads, B), dim3(kVitTcThreads),
+                            kVitTcSmemBytes, st, tm_qkv, e->v_attn, P, C, scale_log2));
+      else
+        VLO_CUDA(launch_pdl(vit_attn_kernel, dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), dim3(kVitThreads), kVitSmemBytes, st,
+                            tm_qkv, e->v_attn, P, C, scale_log2));
+      prof_end(st);
+      count_launch();
+      if (gemm2(e->v_attn, v.out_w, C, C, e->v_h, v.out_b, ACT_NONE, 1)) return -1;
+      if (plain_ln(v.ln2_w, v.ln2_b, nullptr)) return -1;
+      if (gemm2(e->v_xn, v.fc1_w, M, C, e->v_mlp, v.fc1_b, ACT_GELU_TANH, 0)) return -1;
+      if (gemm2(e->v_mlp, v.fc2_w, C, M, e->v_h, v.fc2_b, ACT_NONE, 1)) return -1;
+      const bool last2 = (l == c.vit_layers - 1);
+      if (plain_ln(last2 ? e->post_ln_w : e->vit[l + 1].ln1_w, last2 ? e->post_ln_b : e->vit[l + 1].ln1_b, last2 ? e->v_ln32 : nullptr))
+        return -1;
+      continue;
+    }
     if (tiles_gemm(e->v_xn, v.qkv_w, 3 * C, C, e->v_qkv, v.qkv_b, ACT_NONE)) return -1;
     prof_begin(PROF_VIT_ATTN, st, 4.0 * rows * C * 2);
     if (attn_tc)

@@ -4,6 +4,7 @@
 #include "gemm.cuh"
 #include "gemm_ws.cuh"
 #include "gemm_wsf.cuh"
+#include "gemm2.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -383,6 +384,51 @@ int gemm_wsf_launch(const GemmWsfArgs& a, const void* w, const void* x, int epi,
   if (bn == 32) return launch_wsf_epi<32, ws_default_stages(32)>(epi, tw, tx, a, stream);
   if (bn == 64) return launch_wsf_epi<64, ws_default_stages(64)>(epi, tw, tx, a, stream);
   return launch_wsf_epi<128, ws_default_stages(128)>(epi, tw, tx, a, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-CTA tensor-bound GEMM (gemm2.cuh)
+namespace {
+template <int BN, int STAGES, int EPI>
+int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const Gemm2Args& a, cudaStream_t stream) {
+  auto kern = gemm2_kernel<BN, STAGES, EPI>;
+  using Cfg = Gemm2Cfg<BN, STAGES>;
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes)) return -1;
+  const int tiles = a.m_tiles * a.n_tiles;
+  const int n_pairs = std::min(num_sms() / 2, tiles);
+  if (prof_on())
+    prof_begin(PROF_GEMM_VIT, stream, 2.0 * a.k * (static_cast<double>(a.rows_w) + a.rows_x) + (EPI == G2_STORE16 ? 2.0 : 8.0) * a.rows_x * a.rows_w);
+  VLO_CUDA(launch_pdl(kern, dim3(2 * n_pairs), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tx, tw, a));
+  prof_end(stream);
+  count_launch();
+  return 0;
+}
+}  // namespace
+
+int gemm2_launch(const Gemm2Call& c, cudaStream_t stream) {
+  VLO_CHECK(c.k > 0 && c.k % kGemmBK == 0, "gemm2: K must be a positive multiple of 64");
+  VLO_CHECK(c.rows_x > 0 && c.rows_w > 0 && c.rows_w % 32 == 0, "gemm2: rows_w must be a positive multiple of 32");
+  VLO_CHECK(c.bn == 256 || c.bn == 128, "gemm2: bn is 256 or 128");
+  VLO_CHECK(c.bias != nullptr && (reinterpret_cast<uintptr_t>(c.bias) & 15) == 0, "gemm2: bias required, 16-byte aligned");
+  VLO_CHECK(c.ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(c.out) & 15) == 0, "gemm2: output rows must be 16-byte aligned");
+  Gemm2Args a{};
+  a.rows_x = c.rows_x;
+  a.rows_w = c.rows_w;
+  a.k = c.k;
+  a.m_tiles = (c.rows_x + 255) / 256;
+  a.n_tiles = (c.rows_w + c.bn - 1) / c.bn;
+  a.out = c.out;
+  a.ld_out = c.ld_out;
+  a.bias = c.bias;
+  a.act = c.act;
+  CUtensorMap tx, tw;
+  if (get_tmap(c.x, c.rows_x, c.k, 128, FMT_F16, &tx) != 0) return -1;
+  if (get_tmap(c.w, c.rows_w, c.k, c.bn / 2, FMT_F16, &tw) != 0) return -1;
+  if (c.bn == 256 && c.epi == G2_STORE16) return launch_gemm2<256, 6, G2_STORE16>(tx, tw, a, stream);
+  if (c.bn == 128 && c.epi == G2_STORE16) return launch_gemm2<128, 8, G2_STORE16>(tx, tw, a, stream);
+  if (c.bn == 256 && c.epi == G2_RESID32) return launch_gemm2<256, 6, G2_RESID32>(tx, tw, a, stream);
+  if (c.bn == 128 && c.epi == G2_RESID32) return launch_gemm2<128, 8, G2_RESID32>(tx, tw, a, stream);
+  return fail("gemm2_launch: no kernel instance");
 }
 
 }  // namespace vlo

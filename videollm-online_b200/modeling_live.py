@@ -330,6 +330,13 @@ def _load_checkpoints(cfg, llm_pretrained, adapter, with_vision, device, max_pos
         ad = {}
         for f in sorted(glob.glob(os.path.join(adapter, "*.safetensors"))):
             ad.update(load_file(f))
+        # the adapter's own hyper-parameters win over the CLI defaults (PEFT writes them next to the weights)
+        acfg = os.path.join(adapter, "adapter_config.json")
+        if os.path.isfile(acfg):
+            import json
+            with open(acfg) as fh:
+                aj = json.load(fh)
+            lora_r, lora_alpha = int(aj.get("r", lora_r)), float(aj.get("lora_alpha", lora_alpha))
         sd = W.merge_lora(sd, ad, lora_alpha=lora_alpha, lora_r=lora_r)
     packed = W.pack_llm_for_engine(cfg, sd, device, max_positions)
     if with_vision:
