@@ -148,7 +148,7 @@ def _py_sk_planes(rows_w, k, G):
 
 
 @pytest.mark.parametrize("T,N,K,G", [(11, 6144, 4096, 0), (11, 4096, 14336, 0), (11, 28672, 4096, 0), (1, 512, 256, 0),
-                                     (33, 1000, 1024, 7), (128, 640, 4096, 148), (11, 256, 128, 148)])
+                                     (33, 1000, 1024, 7), (128, 640, 4096, 148), (11, 256, 128, 148), (88, 4096, 4096, 0), (90, 1024, 512, 37)])
 def test_gemm_ws_streamk_partials(lib, T, N, K, G):
     """persistent stream-K weight-streaming GEMM: planes sum to X W^T; decomposition covers every unit once"""
     from videollm_online_b200._lib import check

@@ -17,7 +17,7 @@ else
 export VLO_VIT_GEMM2=0
 fi
 echo "=== [2] fused-GEMM ring depth"
-for s in "VLO_WSF_STAGES=6" "VLO_WSF_STAGES=5" "VLO_WSF_STAGES=4" "VLO_FUSE=0" "VLO_FUSE=0 VLO_WS_STAGES=5"; do
+for s in "VLO_WSF_STAGES=6" "VLO_WSF_STAGES=5" "VLO_WSF_STAGES=4" "VLO_FUSE=0" "VLO_FUSE=0 VLO_WS_STAGES=5" "VLO_FUSE=0 VLO_WS_STAGES=11"; do
   env $s VLO_ATTN=2 VLO_VIT_ATTN=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null | python -c "
 import sys, json
 for line in sys.stdin:

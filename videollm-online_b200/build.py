@@ -42,8 +42,16 @@ def _stale(target: pathlib.Path, deps: list[pathlib.Path]) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> pathlib.Path:
+    """debug=True: a second library (libvlo_b200_dbg.so, objects in build_dbg/) whose bounded mbarrier waits trap after
+    2^16 polls instead of 2^24, so a protocol dead-lock reports the stuck (block, thread) within seconds; select it with
+    VLO_LIB=.../libvlo_b200_dbg.so."""
+    global OBJ, LIB
     nvcc = _nvcc()
+    flags_extra = []
+    if debug:
+        OBJ, LIB = PKG / "build_dbg", PKG / "libvlo_b200_dbg.so"
+        flags_extra = ["-DVLO_MBAR_BOUND_LOG2=16"]
     OBJ.mkdir(exist_ok=True)
     headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted(INCLUDE.glob("*.h"))
     sources = sorted(CSRC.glob("*.cu"))
@@ -53,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
         obj = OBJ / (src.stem + ".o")
         objs.append(obj)
         if force or _stale(obj, [src, *headers, pathlib.Path(__file__)]):
-            jobs.append([nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-I", str(CSRC), "-c", str(src), "-o", str(obj)])
+            jobs.append([nvcc, *NVCC_FLAGS, *flags_extra, "-I", str(INCLUDE), "-I", str(CSRC), "-c", str(src), "-o", str(obj)])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -71,4 +79,4 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv))

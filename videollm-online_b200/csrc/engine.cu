@@ -13,6 +13,7 @@
 #include "gemm_wsf.cuh"
 #include "vit_kernels.cuh"
 #include "vit_attn_tc.cuh"
+#include "vit_attn_tc2.cuh"
 #include "vlo_b200.h"
 
 using namespace vlo;
@@ -640,13 +641,35 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
   static int vit_attn_gen = -1;
   if (vit_attn_gen < 0) {
     const char* ev = getenv("VLO_VIT_ATTN");
-    vit_attn_gen = (ev != nullptr && ev[0] == '1') ? 1 : 2;
+    vit_attn_gen = (ev != nullptr && ev[0] == '1') ? 1 : ((ev != nullptr && ev[0] == '2') ? 2 : 3);
   }
-  const bool attn_tc = vit_attn_gen == 2 && (P + kVitTcBlk - 1) / kVitTcBlk <= kVitTcMaxBlk;
+  const bool attn_tc = vit_attn_gen >= 2 && (P + kVitTcBlk - 1) / kVitTcBlk <= kVitTcMaxBlk;
+  // generation 3 (vit_attn_tc2.cuh): two query tiles in flight per CTA, K / V loaded once per CTA.  Query tiles per CTA:
+  // as many as keeps >= ~120 CTAs in the grid (all 5 at batch 8: one CTA per (frame, head)).
+  const bool attn_tc2 = attn_tc && vit_attn_gen == 3;
+  const int vit_qtiles = (P + 127) / 128;
+  int vit_tpc = vit_qtiles;
+  while (vit_tpc > 2 && c.vit_heads * B * ((vit_qtiles + vit_tpc - 1) / vit_tpc) < 120) --vit_tpc;
+  if (attn_tc2 && ensure_max_smem(reinterpret_cast<const void*>(vit_attn_tc2_kernel), kVit2SmemBytes)) return -1;
   CUtensorMap tm_qkv;
   if (tmap_2d_sw128(e->v_qkv, rows, 3 * C, attn_tc ? kVitTcBlk : kVitBlk, FMT_F16, &tm_qkv)) return -1;
-  if (attn_tc && ensure_max_smem(reinterpret_cast<const void*>(vit_attn_tc_kernel), kVitTcSmemBytes)) return -1;
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // head_dim 64
+  auto launch_vit_attn = [&]() -> int {
+    prof_begin(PROF_VIT_ATTN, st, 4.0 * rows * C * 2);
+    if (attn_tc2)
+      VLO_CUDA(launch_pdl(vit_attn_tc2_kernel, dim3((vit_qtiles + vit_tpc - 1) / vit_tpc, c.vit_heads, B), dim3(kVit2Threads),
+                          kVit2SmemBytes, st, tm_qkv, e->v_attn, P, C, scale_log2, vit_tpc));
+    else if (attn_tc)
+      VLO_CUDA(launch_pdl(vit_attn_tc_kernel, dim3((P + kVitTcBlk - 1) / kVitTcBlk, c.vit_heads, B), dim3(kVitTcThreads),
+                          kVitTcSmemBytes, st, tm_qkv, e->v_attn, P, C, scale_log2));
+    else
+      VLO_CUDA(launch_pdl(vit_attn_kernel, dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), dim3(kVitThreads), kVitSmemBytes, st,
+                          tm_qkv, e->v_attn, P, C, scale_log2));
+    prof_end(st);
+    count_launch();
+    return 0;
+  };
+  if (attn_tc && ensure_max_smem(reinterpret_cast<const void*>(vit_attn_tc_kernel), kVitTcSmemBytes)) return -1;
   // Trunk GEMMs on the persistent swap-AB kernel (weights ride MMA-M, the 576*B token rows are tiled along
   // MMA-N): QKV and fc1 run whole tiles with the fused bias / GELU fp16 epilogue; out_proj and fc2 (few
   // output tiles) run stream-K over all SMs and their partial planes are folded into the fp32 residual
@@ -780,15 +803,7 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     SkCall sc{};
     if (pair_gemm) {
       if (gemm2(e->v_xn, v.qkv_w, 3 * C, C, e->v_qkv, v.qkv_b, ACT_NONE, 0)) return -1;
-      prof_begin(PROF_VIT_ATTN, st, 4.0 * rows * C * 2);
-      if (attn_tc)
-        VLO_CUDA(launch_pdl(vit_attn_tc_kernel, dim3((P + kVitTcBlk - 1) / kVitTcBlk, c.vit_heads, B), dim3(kVitTcThreads),
-                            kVitTcSmemBytes, st, tm_qkv, e->v_attn, P, C, scale_log2));
-      else
-        VLO_CUDA(launch_pdl(vit_attn_kernel, dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), dim3(kVitThreads), kVitSmemBytes, st,
-                            tm_qkv, e->v_attn, P, C, scale_log2));
-      prof_end(st);
-      count_launch();
+      if (launch_vit_attn()) return -1;
       if (gemm2(e->v_attn, v.out_w, C, C, e->v_h, v.out_b, ACT_NONE, 1)) return -1;
       if (plain_ln(v.ln2_w, v.ln2_b, nullptr)) return -1;
       if (gemm2(e->v_xn, v.fc1_w, M, C, e->v_mlp, v.fc1_b, ACT_GELU_TANH, 0)) return -1;
@@ -799,15 +814,7 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
       continue;
     }
     if (tiles_gemm(e->v_xn, v.qkv_w, 3 * C, C, e->v_qkv, v.qkv_b, ACT_NONE)) return -1;
-    prof_begin(PROF_VIT_ATTN, st, 4.0 * rows * C * 2);
-    if (attn_tc)
-      VLO_CUDA(launch_pdl(vit_attn_tc_kernel, dim3((P + kVitTcBlk - 1) / kVitTcBlk, c.vit_heads, B), dim3(kVitTcThreads),
-                          kVitTcSmemBytes, st, tm_qkv, e->v_attn, P, C, scale_log2));
-    else
-      VLO_CUDA(launch_pdl(vit_attn_kernel, dim3((P + kVitBlk - 1) / kVitBlk, c.vit_heads, B), dim3(kVitThreads), kVitSmemBytes, st,
-                          tm_qkv, e->v_attn, P, C, scale_log2));
-    prof_end(st);
-    count_launch();
+    if (launch_vit_attn()) return -1;
     if (partial_gemm(e->v_attn, v.out_w, C, &sc)) return -1;
     if (fix_ln(sc, v.out_b, v.ln2_w, v.ln2_b, nullptr)) return -1;
     if (tiles_gemm(e->v_xn, v.fc1_w, M, C, e->v_mlp, v.fc1_b, ACT_GELU_TANH)) return -1;

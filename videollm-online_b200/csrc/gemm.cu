@@ -277,7 +277,10 @@ int gemm_ws_plan(int rows_w, int k, int mode, int n_ctas, SkInfo* sk, int* max_p
 int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream) {
   VLO_CHECK(c.k > 0 && c.k % kGemmBK == 0, "K must be a positive multiple of 64");
   VLO_CHECK(c.rows_w > 0 && c.rows_x > 0, "empty GEMM operand");
-  const int bn = c.bn > 0 ? c.bn : (c.rows_x <= 16 ? 16 : (c.rows_x <= 32 ? 32 : (c.rows_x <= 64 ? 64 : 128)));
+  // token-tile width: the smallest instance covering rows_x (a narrower X tile leaves more of the ring to the weight stream:
+  // 88 tokens = 8 streams x 11 take the 96-wide instance, 7 x 28 KB stages instead of 6 x 32 KB)
+  const int bn = c.bn > 0 ? c.bn
+                          : (c.rows_x <= 16 ? 16 : (c.rows_x <= 32 ? 32 : (c.rows_x <= 64 ? 64 : ((c.rows_x <= 96 && c.fmt == FMT_BF16) ? 96 : 128))));
   const int x_tiles = (c.rows_x + bn - 1) / bn;
   VLO_CHECK(c.sk.U == static_cast<long long>((c.rows_w + kGemmBM - 1) / kGemmBM) * x_tiles * (c.k / kGemmBK),
             "gemm_ws: plan does not match the call (x_tiles / bn)");
@@ -324,6 +327,7 @@ int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream) {
   VLO_WS_CASE(FMT_BF16, 16)
   VLO_WS_CASE(FMT_BF16, 32)
   VLO_WS_CASE(FMT_BF16, 64)
+  VLO_WS_CASE(FMT_BF16, 96)
   VLO_WS_CASE(FMT_BF16, 128)
   VLO_WS_CASE(FMT_F16, 16)
   VLO_WS_CASE(FMT_F16, 32)
@@ -363,7 +367,7 @@ int gemm_wsf_launch(const GemmWsfArgs& a, const void* w, const void* x, int epi,
   VLO_CHECK(a.k > 0 && a.k % kGemmBK == 0, "K must be a positive multiple of 64");
   VLO_CHECK(a.rows_w > 0 && a.rows_x > 0 && a.rows_x <= 128, "gemm_wsf: 1..128 token rows");
   VLO_CHECK(epi == WSF_RESID || a.rows_w % kGemmBM == 0, "gemm_wsf: QKV / SwiGLU epilogues need whole 128-row tiles");
-  const int bn = a.rows_x <= 16 ? 16 : (a.rows_x <= 32 ? 32 : (a.rows_x <= 64 ? 64 : 128));
+  const int bn = a.rows_x <= 16 ? 16 : (a.rows_x <= 32 ? 32 : (a.rows_x <= 64 ? 64 : (a.rows_x <= 96 ? 96 : 128)));
   VLO_CHECK(a.sk.U == static_cast<long long>((a.rows_w + kGemmBM - 1) / kGemmBM) * (a.k / kGemmBK), "gemm_wsf: plan mismatch");
   CUtensorMap tw, tx;
   if (get_tmap(w, a.rows_w, a.k, kGemmBM, FMT_BF16, &tw) != 0) return -1;
@@ -383,14 +387,46 @@ int gemm_wsf_launch(const GemmWsfArgs& a, const void* w, const void* x, int epi,
   }
   if (bn == 32) return launch_wsf_epi<32, ws_default_stages(32)>(epi, tw, tx, a, stream);
   if (bn == 64) return launch_wsf_epi<64, ws_default_stages(64)>(epi, tw, tx, a, stream);
+  if (bn == 96) return launch_wsf_epi<96, 6>(epi, tw, tx, a, stream);
   return launch_wsf_epi<128, ws_default_stages(128)>(epi, tw, tx, a, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
 // 2-CTA tensor-bound GEMM (gemm2.cuh)
 namespace {
+// output map for the TMA-store epilogue: [rows, cols] row-major, 2- or 4-byte elements, box = 128 rows x 128 bytes, 128B swizzle
+int tmap_out_sw128(const void* ptr, int rows, int cols, int elem_bytes, CUtensorMap* out) {
+  TmapKey key{ptr, rows, cols, -128, 100 + elem_bytes};
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeFn enc = get_encode();
+  if (enc == nullptr) return fail("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail("TMA operand not 16-byte aligned");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (output) failed, CUresult " + std::to_string(r));
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    g_tmaps.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
 template <int BN, int STAGES, int EPI>
-int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const Gemm2Args& a, cudaStream_t stream) {
+int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& to, const Gemm2Args& a, cudaStream_t stream) {
   auto kern = gemm2_kernel<BN, STAGES, EPI>;
   using Cfg = Gemm2Cfg<BN, STAGES>;
   if (ensure_max_smem(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes)) return -1;
@@ -398,7 +434,24 @@ int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const Gemm2Args& 
   const int n_pairs = std::min(num_sms() / 2, tiles);
   if (prof_on())
     prof_begin(PROF_GEMM_VIT, stream, 2.0 * a.k * (static_cast<double>(a.rows_w) + a.rows_x) + (EPI == G2_STORE16 ? 2.0 : 8.0) * a.rows_x * a.rows_w);
-  VLO_CUDA(launch_pdl(kern, dim3(2 * n_pairs), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tx, tw, a));
+  // VLO_GEMM2_PDL bit 0: launch with the programmatic-serialization attribute (prologue - barrier init, TMEM allocation of
+  // the pair, cluster sync - overlaps the predecessor's tail); bit 1: trigger the successor early.  Default 1.  Measured
+  // (tools/gpu_r2_call11.sh, ViT alone at batch 8): 0 -> 5.07 ms, 2 -> 5.10, 1 -> 4.83; 3 DEAD-LOCKS next to the
+  // non-cluster kernels of the trunk (three kernels deep: a cluster kernel resident early AND its successor resident early;
+  // the gemm2 <-> gemm2 chain alone runs), so a cluster kernel here never triggers early.
+  static int pdl_mode = -1;
+  if (pdl_mode < 0) {
+    const char* e = getenv("VLO_GEMM2_PDL");
+    pdl_mode = e ? atoi(e) : 1;
+  }
+  Gemm2Args a2 = a;
+  a2.pdl_trigger = (pdl_mode & 2) ? 1 : 0;
+  if (pdl_mode & 1) {
+    VLO_CUDA(launch_pdl(kern, dim3(2 * n_pairs), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tx, tw, to, a2));
+  } else {
+    kern<<<dim3(2 * n_pairs), dim3(kGemmThreads), Cfg::kSmemBytes, stream>>>(tx, tw, to, a2);
+    VLO_LAUNCH_CHECK();
+  }
   prof_end(stream);
   count_launch();
   return 0;
@@ -407,7 +460,7 @@ int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const Gemm2Args& 
 
 int gemm2_launch(const Gemm2Call& c, cudaStream_t stream) {
   VLO_CHECK(c.k > 0 && c.k % kGemmBK == 0, "gemm2: K must be a positive multiple of 64");
-  VLO_CHECK(c.rows_x > 0 && c.rows_w > 0 && c.rows_w % 32 == 0, "gemm2: rows_w must be a positive multiple of 32");
+  VLO_CHECK(c.rows_x > 0 && c.rows_w > 0 && c.rows_w % 64 == 0, "gemm2: rows_w must be a positive multiple of 64");
   VLO_CHECK(c.bn == 256 || c.bn == 128, "gemm2: bn is 256 or 128");
   VLO_CHECK(c.bias != nullptr && (reinterpret_cast<uintptr_t>(c.bias) & 15) == 0, "gemm2: bias required, 16-byte aligned");
   VLO_CHECK(c.ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(c.out) & 15) == 0, "gemm2: output rows must be 16-byte aligned");
@@ -424,10 +477,14 @@ int gemm2_launch(const Gemm2Call& c, cudaStream_t stream) {
   CUtensorMap tx, tw;
   if (get_tmap(c.x, c.rows_x, c.k, 128, FMT_F16, &tx) != 0) return -1;
   if (get_tmap(c.w, c.rows_w, c.k, c.bn / 2, FMT_F16, &tw) != 0) return -1;
-  if (c.bn == 256 && c.epi == G2_STORE16) return launch_gemm2<256, 6, G2_STORE16>(tx, tw, a, stream);
-  if (c.bn == 128 && c.epi == G2_STORE16) return launch_gemm2<128, 8, G2_STORE16>(tx, tw, a, stream);
-  if (c.bn == 256 && c.epi == G2_RESID32) return launch_gemm2<256, 6, G2_RESID32>(tx, tw, a, stream);
-  if (c.bn == 128 && c.epi == G2_RESID32) return launch_gemm2<128, 8, G2_RESID32>(tx, tw, a, stream);
+  CUtensorMap to;
+  VLO_CHECK(c.ld_out == c.rows_w, "gemm2: the output is a dense [rows_x, rows_w] matrix");
+  if (tmap_out_sw128(c.out, c.rows_x, c.rows_w, c.epi == G2_STORE16 ? 2 : 4, &to) != 0) return -1;
+  // ring: 5 x 32 KB (bn 256) / 7 x 24 KB (bn 128) + two 16 KB output panels
+  if (c.bn == 256 && c.epi == G2_STORE16) return launch_gemm2<256, 5, G2_STORE16>(tx, tw, to, a, stream);
+  if (c.bn == 128 && c.epi == G2_STORE16) return launch_gemm2<128, 7, G2_STORE16>(tx, tw, to, a, stream);
+  if (c.bn == 256 && c.epi == G2_RESID32) return launch_gemm2<256, 5, G2_RESID32>(tx, tw, to, a, stream);
+  if (c.bn == 128 && c.epi == G2_RESID32) return launch_gemm2<128, 7, G2_RESID32>(tx, tw, to, a, stream);
   return fail("gemm2_launch: no kernel instance");
 }
 

@@ -33,6 +33,7 @@ struct Gemm2Args {
   int ld_out;
   const float* bias;      // [rows_w]
   int act;
+  int pdl_trigger;        // 1: let the successor kernel start its prologue early (griddepcontrol.launch_dependents)
 };
 
 template <int BN, int STAGES>
@@ -41,7 +42,8 @@ struct Gemm2Cfg {
   static constexpr int kBytesA = 128 * kGemmBK * 2;
   static constexpr int kBytesB = (BN / 2) * kGemmBK * 2;
   static constexpr int kTmemCols = 2 * BN;          // two accumulator buffers (256 or 512 columns)
-  static constexpr int kSmemBytes = kStages * (kBytesA + kBytesB) + 1024 + 512;
+  static constexpr int kStoreBytes = 128 * 128;     // one output panel: 128 token rows x 128 bytes, 128B-swizzled
+  static constexpr int kSmemBytes = kStages * (kBytesA + kBytesB) + 2 * kStoreBytes + 1024 + 512;
 };
 
 // ------------------------------------------------------------------ cluster / cta_group::2 wrappers
@@ -97,16 +99,40 @@ __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
+// ---- epilogue through shared memory + TMA store (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void g2_epi_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 template <int BN, int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Gemm2Args p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+             const __grid_constant__ CUtensorMap tm_out, const Gemm2Args p) {
   using Cfg = Gemm2Cfg<BN, STAGES>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + S * Cfg::kBytesA;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * (Cfg::kBytesA + Cfg::kBytesB));   // used in the leader only
+  uint8_t* smem_out = smem + S * (Cfg::kBytesA + Cfg::kBytesB);      // two output panels (ping-pong)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_out + 2 * Cfg::kStoreBytes);   // used in the leader only
   uint64_t* empty_bar = full_bar + S;
   uint64_t* acc_full = empty_bar + S;    // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]  used in the leader only: 4 epilogue warps x 2 CTAs
@@ -122,6 +148,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_out);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -137,8 +164,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   cluster_sync_all();     // both CTAs' barriers are initialised and both halves of the TMEM allocation are done
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_trigger();          // after the TMEM allocation (see gemm_ws.cuh)
-  pdl_wait();             // X is the predecessor's output
+  if (p.pdl_trigger) pdl_trigger();   // after the TMEM allocation (see gemm_ws.cuh)
+  pdl_wait();             // X is the predecessor's output (no-op when launched without the PDL attribute)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -186,64 +213,81 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     }
   } else {
     // -------------------------------------------------- epilogue warps 2..5 (both CTAs): thread = token row
+    // TMEM -> registers -> bias / activation / rounding -> 128B-swizzled panel in shared memory -> ONE TMA store (or TMA
+    // reduce-add into the fp32 residual stream) per 128-byte-wide panel: full-line writes issued by the copy engine instead
+    // of 32 strided 16-byte stores per warp instruction (which made the epilogue, not the MMA, the critical path).
+    constexpr int kPanelCols = (EPI == G2_STORE16) ? 64 : 32;       // 128 bytes per row
     const int q = warp & 3;
-    int item = 0;
+    const int r = q * 32 + lane;                                     // row inside this CTA's 128-row half tile
+    const bool store_thread = (warp == 2 && lane == 0);
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    int item = 0, pbuf = 0;
     for (int t = pair; t < tiles; t += n_pairs, ++item) {
       const int mt = t % p.m_tiles, nt = t / p.m_tiles;
       const int buf = item & 1;
       mbar_wait(&acc_full[buf], (item >> 1) & 1);
       tc_fence_after();
-      const int row = mt * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
-      const bool row_ok = row < p.rows_x;
+      const int row0 = mt * 256 + static_cast<int>(rank) * 128;
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tacc + static_cast<uint32_t>(c0), v);
-        tmem_ld_wait();
-        if (c0 + 32 >= BN) {   // last chunk is in registers: hand the accumulator buffer back to the leader's MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&acc_empty[buf]), 0));
+      for (int c0 = 0; c0 < BN; c0 += kPanelCols, pbuf ^= 1) {
+        const uint32_t sb = smem_u32(smem_out + pbuf * Cfg::kStoreBytes) + static_cast<uint32_t>(r) * 128u;
+        if (store_thread) bulk_wait_group_read<1>();   // the store issued from this buffer two panels ago has read it
+        g2_epi_sync();
+#pragma unroll
+        for (int hh = 0; hh < kPanelCols / 32; ++hh) {
+          uint32_t v[32];
+          tmem_ld_x32(tacc + static_cast<uint32_t>(c0 + 32 * hh), v);
+          tmem_ld_wait();
+          if (c0 + 32 * hh + 32 >= BN) {   // last chunk is in registers: hand the accumulator buffer back to the leader's MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&acc_empty[buf]), 0));
+          }
+          const int n0 = nt * BN + c0 + 32 * hh;
+          float x[32];
+          if (n0 < p.rows_w) {              // rows_w is a multiple of 32: a chunk is whole or absent
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+              x[4 * i] = fp16_round(__uint_as_float(v[4 * i]) + b.x);
+              x[4 * i + 1] = fp16_round(__uint_as_float(v[4 * i + 1]) + b.y);
+              x[4 * i + 2] = fp16_round(__uint_as_float(v[4 * i + 2]) + b.z);
+              x[4 * i + 3] = fp16_round(__uint_as_float(v[4 * i + 3]) + b.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = 0.f;
+          }
+          if (EPI == G2_STORE16) {
+            if (p.act != ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) x[i] = apply_act<FMT_F16>(x[i], p.act);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {   // 16-byte chunk (hh * 4 + i) of the row, XOR-swizzled with the row index
+              __half2 h0 = __floats2half2_rn(x[8 * i], x[8 * i + 1]), h1 = __floats2half2_rn(x[8 * i + 2], x[8 * i + 3]);
+              __half2 h2 = __floats2half2_rn(x[8 * i + 4], x[8 * i + 5]), h3 = __floats2half2_rn(x[8 * i + 6], x[8 * i + 7]);
+              st_shared_v4(sb + ((static_cast<uint32_t>(hh * 4 + i) ^ sw) << 4), *reinterpret_cast<uint32_t*>(&h0),
+                           *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            }
+          } else {   // G2_RESID32: fp32 panel, added into the residual stream by the copy engine (HF:...siglip.py:353, 360)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              st_shared_v4(sb + ((static_cast<uint32_t>(i) ^ sw) << 4), __float_as_uint(x[4 * i]), __float_as_uint(x[4 * i + 1]),
+                           __float_as_uint(x[4 * i + 2]), __float_as_uint(x[4 * i + 3]));
+          }
         }
-        const int n0 = nt * BN + c0;
-        if (!row_ok || n0 >= p.rows_w) continue;     // rows_w is a multiple of 32: a chunk is whole or absent
-        float x[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
-          x[4 * i] = fp16_round(__uint_as_float(v[4 * i]) + b.x);
-          x[4 * i + 1] = fp16_round(__uint_as_float(v[4 * i + 1]) + b.y);
-          x[4 * i + 2] = fp16_round(__uint_as_float(v[4 * i + 2]) + b.z);
-          x[4 * i + 3] = fp16_round(__uint_as_float(v[4 * i + 3]) + b.w);
-        }
-        if (EPI == G2_STORE16) {
-          if (p.act != ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = apply_act<FMT_F16>(x[i], p.act);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ld_out + n0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __half2 h0 = __floats2half2_rn(x[8 * i], x[8 * i + 1]), h1 = __floats2half2_rn(x[8 * i + 2], x[8 * i + 3]);
-            __half2 h2 = __floats2half2_rn(x[8 * i + 4], x[8 * i + 5]), h3 = __floats2half2_rn(x[8 * i + 6], x[8 * i + 7]);
-            dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-          }
-        } else {   // G2_RESID32: fp32 residual stream += fp16(Linear output)   (HF:...siglip.py:353, 360)
-          float4* hp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ld_out + n0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 h = hp[i];
-            h.x += x[4 * i];
-            h.y += x[4 * i + 1];
-            h.z += x[4 * i + 2];
-            h.w += x[4 * i + 3];
-            hp[i] = h;
-          }
+        fence_proxy_async();      // generic-proxy writes -> visible to the async proxy (TMA)
+        g2_epi_sync();
+        if (store_thread) {
+          if (EPI == G2_STORE16) tma_store_2d(&tm_out, smem_out + pbuf * Cfg::kStoreBytes, nt * BN + c0, row0);
+          else tma_reduce_add_2d(&tm_out, smem_out + pbuf * Cfg::kStoreBytes, nt * BN + c0, row0);
+          bulk_commit_group();
         }
       }
     }
+    if (store_thread) bulk_wait_group_all();
     tc_fence_before();
   }
   // teardown: nobody may free the pair's TMEM (or exit with a peer still multicasting into its barriers) early

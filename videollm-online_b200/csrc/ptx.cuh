@@ -54,12 +54,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifndef VLO_MBAR_BOUND_LOG2
+#define VLO_MBAR_BOUND_LOG2 24   // debug builds (build.py --debug -> libvlo_b200_dbg.so, VLO_LIB=...) use 16: a stuck wait traps within seconds
+#endif
 // Bounded wait: a protocol bug must trap (the launch fails loudly) instead of
 // hanging the GPU.  try_wait suspends in hardware, so the bound is generous.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
+    if (++spins > (1u << VLO_MBAR_BOUND_LOG2)) {
       printf("vlo: mbarrier timeout block(%d,%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, parity);
       __trap();
