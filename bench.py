@@ -41,7 +41,8 @@ def static_config(world: int) -> dict:
             "parallelism": f"replicas x{world} (weights broadcast at init, no hot-path collective)",
             "l2": "inputs larger than L2: every step streams 15.0 GB of weights + 1.6 GB of KV (L2 = 126 MB)",
             "pipelining": "ViT+connector of the NEXT frames on a side CUDA stream during the decoder steps of the current ones "
-                          "(same work per frame; --encode-ahead frames per ViT pass, default 4)"}
+                          "(same work per frame; --encode-ahead frames per ViT pass, default 1: the next frame, as a live "
+                          "camera delivers it)"}
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -469,9 +470,9 @@ def run_engine_arm(args):
                 "method": "CUDA events around 4 back-to-back passes of the 128 decoder GEMM launches (q|k|v, o, gate|up, down of all 32 layers) on the engine's buffers, T=11",
                 "in_step_event_bracketed": {"achieved": gs["achieved_gbs"], "avg_us_per_launch": gs["avg_us_per_launch"],
                                             "note": "per-launch event pairs inside the step (PDL off): includes ~3-5 us bracket overhead per launch"}}
-        roof_attn = {"bound": "hbm", "kernel": "attn_tc2_kernel + attn_merge_kernel (KV-append attention, tcgen05 with P in TMEM, key-sliced softmax; one launch pair per layer)",
+        roof_attn = {"bound": "hbm", "kernel": "attn_tc_kernel + attn_merge_kernel (KV-append attention on tcgen05, one launch pair per layer; attn_tc2_kernel, P in TMEM + key-sliced softmax, takes over from 24k keys)",
                      "achieved": micro_attn["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": micro_attn["achieved_gbs"] / hbm_peak,
-                     "peak_source": which, "traffic": _ncu_traffic("attn_tc2")[0], "traffic_commit": _ncu_traffic("attn_tc2")[1], "avg_us_per_launch": micro_attn["us_per_launch_incl_merge"],
+                     "peak_source": which, "traffic": _ncu_traffic("attn_tc")[0], "traffic_commit": _ncu_traffic("attn_tc")[1], "avg_us_per_launch": micro_attn["us_per_launch_incl_merge"],
                      "algo_bytes_per_launch": micro_attn["algo_bytes_per_launch"],
                      "method": "CUDA events around 4x32 back-to-back launch pairs over the 32 layers' caches (1.6 GB, > L2), q=11, kv=12011; merge kernel time included",
                      "main_kernel_only": {"achieved": micro_attn["achieved_gbs_main_only"], "frac": micro_attn["achieved_gbs_main_only"] / hbm_peak,
@@ -742,8 +743,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
-    ap.add_argument("--encode-ahead", dest="encode_ahead", type=int, default=4,
-                    help="frames per encode-ahead ViT pass on the side stream (1 = one frame at a time)")
+    ap.add_argument("--encode-ahead", dest="encode_ahead", type=int, default=1,
+                    help="frames per encode-ahead ViT pass on the side stream (1 = one frame at a time: the small-tile ViT "
+                         "co-resides with the decoder step; >= 3 = 2-CTA tensor-bound GEMMs, serialised against the step)")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the side measurements of the other BASELINE configs")
     ap.add_argument("--quick-extras", dest="quick_extras", action="store_true", help="shorter side measurements (dev runs)")
     args = ap.parse_args()

@@ -75,6 +75,10 @@ def traffic(dst, *pairs):
         dur = [float(x[it]) for x in rows]
         out[key] = {"dram_bytes_per_launch": sum(tot) / max(1, len(tot)), "launches": len(tot), "avg_duration_" + units[it]: sum(dur) / max(1, len(dur)),
                     "source": rep.split("/")[-1] + " (ncu --set full --clock-control none, cold cache)"}
+    try:   # stamp the capture with the commit it was taken at (bench.py reports it as traffic_commit)
+        out["commit"] = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    except Exception:
+        pass
     json.dump(out, open(dst, "w"), indent=1)
     print(json.dumps(out, indent=1))
 

@@ -26,14 +26,19 @@ int max_chunks(int total_tokens, int n_seqs, int G) {
 }
 // kernel generation: 3 = tcgen05 with P in TMEM and the deep K/V ring (attn_tc2.cuh, default), 2 = tcgen05 with P in
 // shared memory (attn_tc.cuh), 1 = mma.sync (attn.cuh).  VLO_ATTN=1|2 forces the older kernels (A/B checks).
-int attn_version_impl(int G) {
+// Default (VLO_ATTN unset): by context length.  Same-box A/B (tools/gpu_r2_call6.sh / call7.sh): at 12k keys the two
+// tcgen05 kernels tie in the back-to-back loop (14.6 us) and generation 2 is 9 % faster inside the step (generation 3's
+// 192 KB prefetch before the grid dependency competes with the tail of the QKV GEMM); at 66k keys generation 3 wins
+// (46.1 vs 49.9 us, 0.90 of the HBM peak).
+int attn_version_impl(int G, int max_kv_len = 0) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("VLO_ATTN");
-    forced = (e != nullptr && e[0] == '1') ? 1 : ((e != nullptr && e[0] == '2') ? 2 : 3);
+    forced = (e != nullptr && e[0] == '1') ? 1 : ((e != nullptr && e[0] == '2') ? 2 : ((e != nullptr && e[0] == '3') ? 3 : 0));
   }
   if (128 % G != 0) return 1;
-  return forced;
+  if (forced > 0) return forced;
+  return max_kv_len >= 24576 ? 3 : 2;
 }
 // keys per pipeline block of the v3 kernel (VLO_ATTN_BLK=64|128)
 int attn_tc2_blk() {
@@ -78,7 +83,9 @@ int attn_plan(AttnPlan* plan, void* d_ws, void* h_stage, const AttnSeq* seqs, in
   VLO_CHECK(n_heads % n_kv_heads == 0, "n_heads must be a multiple of n_kv_heads");
   const int G = n_heads / n_kv_heads;
   VLO_CHECK(G <= 64, "GQA group too large");
-  const int version = attn_version_impl(G);
+  int max_kv = 0;
+  for (int s = 0; s < n_seqs; ++s) max_kv = std::max(max_kv, seqs[s].kv_len);
+  const int version = attn_version_impl(G, max_kv);
   const int per = (version >= 2 ? 128 : 64) / G;   // query tokens per work item
   const int blk = version == 3 ? attn_tc2_blk() : (version == 2 ? kTcBlk : kAttnBlk);  // keys per pipeline block
   plan->version = version;

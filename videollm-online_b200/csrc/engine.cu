@@ -40,6 +40,12 @@ size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 struct vlo_engine {
   vlo_config cfg{};
   int device = 0;
+  // Cluster kernels (the 2-CTA ViT GEMMs) never run concurrently with a decoder step: next to the step's deep PDL chain
+  // (several kernels resident early, all SM shared memory taken) a pending CTA pair was observed to stall both streams.
+  // A step enqueued on another stream than the last pair-GEMM ViT pass waits for that pass, and vice versa (events below).
+  cudaEvent_t ev_step = nullptr, ev_pair = nullptr;
+  cudaStream_t step_stream = nullptr, pair_stream = nullptr;
+  bool step_seen = false, pair_seen = false;
   std::map<std::string, std::pair<const void*, int64_t>> tensors;
   bool finalized = false;
 
@@ -161,12 +167,15 @@ int gemm_partial(vlo_engine* e, const bf16* w, int n_out, const bf16* x, int T, 
   return gemm_ws_launch(c, st);
 }
 
-// Fused-finisher switch (default on): VLO_FUSE=0 falls back to stream-K planes + separate fix-up kernels (A/B checks).
+// Fused-finisher switch (VLO_FUSE=1; default off).  Same-box A/B (tools/gpu_r2_call7.sh): the fused chain (8 launches per
+// layer) runs the frame step at 192 frames/s, planes + separate fix-up kernels (10 launches) at 201: a finisher's epilogue
+// (flag acquire -> plane loads -> RoPE table loads -> stores) is a ~3 us tail at the end of EVERY CTA during which the SM
+// streams nothing, while a separate fix-up kernel runs next to the next GEMM's CTA, whose ring is already filling.
 bool fuse_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VLO_FUSE");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }
@@ -395,6 +404,8 @@ int vlo_engine_destroy(vlo_engine* e) {
   if (e->stage) cudaFreeHost(e->stage);
   for (int i = 0; i < kStageSlots; ++i)
     if (e->stage_events[i]) cudaEventDestroy(e->stage_events[i]);
+  if (e->ev_step) cudaEventDestroy(e->ev_step);
+  if (e->ev_pair) cudaEventDestroy(e->ev_pair);
   delete e;
   return 0;
 }
@@ -641,12 +652,16 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
   static int vit_attn_gen = -1;
   if (vit_attn_gen < 0) {
     const char* ev = getenv("VLO_VIT_ATTN");
-    vit_attn_gen = (ev != nullptr && ev[0] == '1') ? 1 : ((ev != nullptr && ev[0] == '2') ? 2 : 3);
+    vit_attn_gen = (ev != nullptr && ev[0] == '1') ? 1 : ((ev != nullptr && ev[0] == '2') ? 2 : ((ev != nullptr && ev[0] == '3') ? 3 : 0));
   }
-  const bool attn_tc = vit_attn_gen >= 2 && (P + kVitTcBlk - 1) / kVitTcBlk <= kVitTcMaxBlk;
+  // default: the two-tile tcgen05 kernel for the tensor-bound batches (>= 3 frames: 0.95 vs 1.2 ms per pass at batch 8),
+  // the mma.sync kernel for 1-2 frames, where a launch is latency-bound (80 CTAs, 12.8 vs 14.7 us) and hidden behind the
+  // decoder step it overlaps
+  const int attn_gen = vit_attn_gen > 0 ? vit_attn_gen : (B >= 3 ? 3 : 1);
+  const bool attn_tc = attn_gen >= 2 && (P + kVitTcBlk - 1) / kVitTcBlk <= kVitTcMaxBlk;
   // generation 3 (vit_attn_tc2.cuh): two query tiles in flight per CTA, K / V loaded once per CTA.  Query tiles per CTA:
   // as many as keeps >= ~120 CTAs in the grid (all 5 at batch 8: one CTA per (frame, head)).
-  const bool attn_tc2 = attn_tc && vit_attn_gen == 3;
+  const bool attn_tc2 = attn_tc && attn_gen == 3;
   const int vit_qtiles = (P + 127) / 128;
   int vit_tpc = vit_qtiles;
   while (vit_tpc > 2 && c.vit_heads * B * ((vit_qtiles + vit_tpc - 1) / vit_tpc) < 120) --vit_tpc;
@@ -775,6 +790,10 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     use_gemm2 = (ev != nullptr && ev[0] == '0') ? 0 : 1;
   }
   const bool pair_gemm = use_gemm2 && B >= 3 && C % 128 == 0 && M % 128 == 0;
+  if (pair_gemm) {
+    if (e->ev_pair == nullptr) VLO_CUDA(cudaEventCreateWithFlags(&e->ev_pair, cudaEventDisableTiming));
+    if (e->step_seen && e->step_stream != st) VLO_CUDA(cudaStreamWaitEvent(st, e->ev_step, 0));   // behind the last decoder step
+  }
   auto gemm2 = [&](const __half* x, const __half* w, int n_out, int k, void* out, const float* bias, int act, int epi) -> int {
     Gemm2Call g{};
     g.x = x;
@@ -825,6 +844,11 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     if (fix_ln(sc, v.fc2_b, last ? e->post_ln_w : e->vit[l + 1].ln1_w, last ? e->post_ln_b : e->vit[l + 1].ln1_b,
                last ? e->v_ln32 : nullptr))
       return -1;
+  }
+  if (pair_gemm) {   // decoder steps on other streams queue behind the trunk's cluster kernels
+    VLO_CUDA(cudaEventRecord(e->ev_pair, st));
+    e->pair_stream = st;
+    e->pair_seen = true;
   }
   const int NT = e->n_frame_tokens;
   const int cls = c.frame_token_cls ? 1 : 0;
@@ -885,6 +909,7 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
   const vlo_config& c = e->cfg;
   VLO_CHECK(n_seqs > 0 && n_seqs <= c.max_streams, "step: n_seqs out of range");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (e->pair_seen && e->pair_stream != st) VLO_CUDA(cudaStreamWaitEvent(st, e->ev_pair, 0));   // see vlo_engine::ev_pair
   const int H = c.hidden_size;
   int T = 0;
   for (int i = 0; i < n_seqs; ++i) {
@@ -1048,6 +1073,10 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
 
   for (int i = 0; i < n_seqs; ++i) e->kv_len[h_stream_ids[i]] += h_q_lens[i];
   e->last_step_tokens = T;
+  if (e->ev_step == nullptr) VLO_CUDA(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
+  VLO_CUDA(cudaEventRecord(e->ev_step, st));
+  e->step_stream = st;
+  e->step_seen = true;
   return 0;
 }
 
