@@ -115,12 +115,13 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU (reference algorithm) arm
-def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 4, vit_layers: int = 6):
+def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 0, vit_layers: int = 0, budget_s: float = 150.0):
     """Times the oracle (CPU port of the reference forward, oracle/vlo_oracle.py) on the host cores.
 
-    Bounded sample per step: the full-size ViT trunk truncated to `vit_layers` of 24 blocks (+ embeddings,
-    head, pool) and the full-width decoder truncated to `dec_layers` of 32 layers over a 12k-token cache
-    (+ final norm, lm_head), each scaled to the full layer count -> seconds per full frame step."""
+    A step is the FULL frame step (24 ViT blocks + connector, 32 decoder layers over a 12k-token cache, lm_head,
+    decision) whenever (n_steps + n_warm) of them fit `budget_s` on this host (probed with one full step): then nothing
+    is extrapolated and ms_per_step x steps is the run's wall time.  On a slower host the stacks are truncated
+    (dec_layers / vit_layers > 0 force that) and the per-layer cost is scaled to the full depth; the line says so."""
     import torch
     # all the host threads it can use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would time the CPU arm
     # on one core; use one thread per physical core (torch's own default outside torchrun)
@@ -156,25 +157,29 @@ def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 4, vit_laye
     sd = {"model.norm.weight": torch.ones(H, dtype=torch.bfloat16), "lm_head.weight": rnd((V, H)),
           "connector.0.weight": rnd((H, cfg.vision_hidden_size)), "connector.0.bias": rnd((H,)),
           "connector.2.weight": rnd((H, H)), "connector.2.bias": rnd((H,))}
-    for i in range(dec_layers):
+    for i in range(cfg.num_hidden_layers):   # every layer aliases the same tensors: full depth costs no extra host memory
         for k, v in layer.items():
             sd[f"model.layers.{i}.{k}"] = v
-    dcfg = dataclasses.replace(cfg, num_hidden_layers=dec_layers)
     kv_block = rnd((1, nkv, KV_START, hd), 1.0)
-    # ---- ViT: full-size SigLIP-L weights for the sampled blocks (fp32, as on a CPU host)
+    # ---- ViT: full-size SigLIP-L blocks (fp32, as on a CPU host); one block's weights aliased for all 24
     from videollm_online_b200 import weights as W
-    vcfg = dataclasses.replace(cfg, vision_num_hidden_layers=vit_layers)
-    vs = {k: v for k, v in W.synthetic_vision_state(vcfg, seed=1).items()}
+    one_blk = dataclasses.replace(cfg, vision_num_hidden_layers=1)
+    vs = {k: v for k, v in W.synthetic_vision_state(one_blk, seed=1).items()}
+    for i in range(1, cfg.vision_num_hidden_layers):
+        for k in [k for k in vs if k.startswith("encoder.layers.0.")]:
+            vs["encoder.layers.%d." % i + k[len("encoder.layers.0."):]] = vs[k]
     frames = torch.randint(0, 256, (1, 3, cfg.frame_resolution, cfg.frame_resolution), dtype=torch.uint8, generator=g)
     ids = torch.tensor([cfg.frame_token_interval_id])
     sd["model.embed_tokens.weight"] = rnd((1024, H), 1.0)  # only row `interval id` is read
 
-    def one_step():
+    def one_step(nd, nv):
+        dcfg = dataclasses.replace(cfg, num_hidden_layers=nd)
+        vcfg = dataclasses.replace(cfg, vision_num_hidden_layers=nv)
         t0 = time.perf_counter()
         fe = O.visual_embed(sd, vs, vcfg, frames)
         t1 = time.perf_counter()
-        cache = O.KVCache(dec_layers)
-        for i in range(dec_layers):
+        cache = O.KVCache(nd)
+        for i in range(nd):
             cache.k[i], cache.v[i] = kv_block, kv_block
         emb = torch.cat([O.embed_tokens(sd, ids), fe], 0)
         t2 = time.perf_counter()
@@ -184,22 +189,34 @@ def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 4, vit_laye
         return t1 - t0, t3 - t2
 
     with torch.no_grad():
+        if dec_layers <= 0 or vit_layers <= 0:
+            one_step(2, 2)                                       # page in MKL / the weights
+            pv, pd = one_step(8, 6)                              # probe: a quarter of the stacks
+            est_full = pv * cfg.vision_num_hidden_layers / 6 + pd * cfg.num_hidden_layers / 8
+            frac = min(1.0, budget_s / (est_full * (n_steps + n_warm)))
+            dec_layers = cfg.num_hidden_layers if frac >= 1.0 else max(4, int(cfg.num_hidden_layers * frac))
+            vit_layers = cfg.vision_num_hidden_layers if frac >= 1.0 else max(3, int(cfg.vision_num_hidden_layers * frac))
         for _ in range(n_warm):
-            one_step()
+            one_step(dec_layers, vit_layers)
         tv, td = [], []
         for _ in range(n_steps):
-            a, b = one_step()
+            a, b = one_step(dec_layers, vit_layers)
             tv.append(a); td.append(b)
+    full = dec_layers == cfg.num_hidden_layers and vit_layers == cfg.vision_num_hidden_layers
     # scale the truncated stacks to the full model (per-layer cost is uniform; embeddings/head/lm_head are
     # counted once at full size inside the sample and slightly over-weighted by the scaling -> conservative for us)
     vit_s = sum(tv) / len(tv) * (cfg.vision_num_hidden_layers / vit_layers)
     dec_s = sum(td) / len(td) * (cfg.num_hidden_layers / dec_layers)
     per_step = [a * (cfg.vision_num_hidden_layers / vit_layers) + b * (cfg.num_hidden_layers / dec_layers) for a, b in zip(tv, td)]
     return vit_s + dec_s, {"vit_s_per_frame": vit_s, "decoder_s_per_step": dec_s, "threads": torch.get_num_threads(),
-                           "per_step_s": [round(x, 3) for x in per_step],
-                           "sample": f"{n_steps} frame steps (+{n_warm} warm-up) of oracle/vlo_oracle.py: full-size SigLIP-L trunk truncated "
-                                     f"to {vit_layers}/24 blocks and Llama-3-8B truncated to {dec_layers}/32 layers at kv={KV_START}, "
-                                     "scaled to the full layer counts; fp32 ViT / bf16 decoder as the reference runs on a CPU host"}
+                           "per_step_s": [round(x, 3) for x in per_step], "extrapolated": not full,
+                           "rel_std": (round(float(torch.tensor(per_step).std() / torch.tensor(per_step).mean()), 4) if len(per_step) > 1 else None),
+                           "sample": (f"{n_steps} FULL frame steps (+{n_warm} warm-up) of oracle/vlo_oracle.py: SigLIP-L 24 blocks + connector + "
+                                      f"Llama-3-8B 32 layers at kv={KV_START} + lm_head + decision, nothing extrapolated" if full else
+                                      f"{n_steps} frame steps (+{n_warm} warm-up) of oracle/vlo_oracle.py with the stacks truncated to "
+                                      f"{vit_layers}/24 ViT blocks and {dec_layers}/32 decoder layers at kv={KV_START} (host too slow for full "
+                                      "steps within the time budget), per-layer cost scaled to the full depth")
+                                     + "; fp32 ViT / bf16 decoder as the reference runs on a CPU host"}
 
 
 def run_reference_arm(args):
@@ -216,7 +233,8 @@ def run_reference_arm(args):
             "config": static_config(int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": info["threads"], "kind": "port", "sample": info["sample"],
                              "vit_s_per_frame": info["vit_s_per_frame"], "decoder_s_per_step": info["decoder_s_per_step"],
-                             "host_cpus": os.cpu_count(), "per_step_s": info["per_step_s"],
+                             "host_cpus": os.cpu_count(), "per_step_s": info["per_step_s"], "extrapolated": info["extrapolated"],
+                             "rel_std": info["rel_std"],
                              "note": "CPU port of the reference forward (oracle/), NOT the reference's GPU path: a reported baseline, not a speed-up claim"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
@@ -712,9 +730,10 @@ def run_engine_arm(args):
     if extras:
         line["extras"] = extras
     if world == 1 and not args.no_cpu_baseline:
-        per_step, info = cpu_reference_times(2, 1)
+        per_step, info = cpu_reference_times(2, 1, budget_s=45.0)
         line["cpu_baseline"] = {"value": 1.0 / per_step, "unit": UNIT, "cores": info["threads"], "kind": "port",
-                                "sample": info["sample"], "host_cpus": os.cpu_count(),
+                                "sample": info["sample"], "host_cpus": os.cpu_count(), "extrapolated": info["extrapolated"],
+                                "per_step_s": info["per_step_s"], "rel_std": info["rel_std"],
                                 "vit_s_per_frame": info["vit_s_per_frame"], "decoder_s_per_step": info["decoder_s_per_step"]}
     if dist is not None:
         dist.destroy_process_group()
