@@ -698,8 +698,16 @@ int vlo_vit_encode(vlo_engine* e, const uint8_t* d_frames, int B, void* d_out, f
     coreside = (ev != nullptr && ev[0] == '0') ? 0 : 1;
   }
   const bool small = coreside && B <= 2;
+  // token-tile width of the co-resident configuration (VLO_VIT_SMALL_BN=64|96; ring = 3 stages of 16 KB + bn * 128 B).
+  // 96 divides the 576 tokens of a frame (no padded tile, 144 tiles = one wave): the pass alone takes 2.22 instead of
+  // 2.46 ms (batch 2: 2.99 vs 3.43); next to the decoder step it is a wash (202-204 frames/s either way).
+  static int small_bn = 0;
+  if (small_bn == 0) {
+    const char* ev = getenv("VLO_VIT_SMALL_BN");
+    small_bn = (ev != nullptr && atoi(ev) == 64) ? 64 : 96;
+  }
   auto pick_bn = [&](int n_out, int mode) {
-    if (small) return 64;
+    if (small) return small_bn;
     const int cands[4] = {64, 96, 128, 192};
     int best = 64;
     double best_eff = -1.0;

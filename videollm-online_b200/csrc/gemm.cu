@@ -315,6 +315,7 @@ int gemm_ws_launch(const GemmWsCall& c, cudaStream_t stream) {
     if (st == 6) return launch_ws<FMT_BF16, 16, 6>(tw, tx, a, stream);
     if (st == 11) return launch_ws<FMT_BF16, 16, 11>(tw, tx, a, stream);
   }
+  if (c.fmt == FMT_F16 && c.small_smem && bn == 96) return launch_ws<FMT_F16, 96, 3>(tw, tx, a, stream);    // 84 KB ring
   if (c.fmt == FMT_F16 && bn == 64 && c.small_smem) {
     static int vst = 0;
     if (vst == 0) {
