@@ -57,6 +57,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef VLO_MBAR_BOUND_LOG2
 #define VLO_MBAR_BOUND_LOG2 24   // debug builds (build.py --debug -> libvlo_b200_dbg.so, VLO_LIB=...) use 16: a stuck wait traps within seconds
 #endif
+// non-blocking probe (mbarrier.test_wait): true when the phase with this parity has completed
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must trap (the launch fails loudly) instead of
 // hanging the GPU.  try_wait suspends in hardware, so the bound is generous.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -6,12 +6,12 @@
 // Why: the one-tile kernel (vit_attn_tc.cuh) is a serial chain per CTA - S MMA -> 128 exponentials per thread -> P -> PV MMA -
 // with the tensor pipe idle during the exponentials and the MUFU idle during the MMAs, one CTA per SM: 15 % tensor-pipe
 // utilisation, 52 us per layer at batch 8 (profiles/r02_vit_b8_singlecta_metrics.csv).  Here two softmax groups (A, B) of
-// 128 threads each own a query tile; the single MMA thread alternates S_A, S_B, PV_A, PV_B, so the MMAs of one tile run
+// 128 threads each own a query tile; the single MMA thread serves both, so the MMAs / TMEM traffic of one tile run
 // under the exponentials of the other, and a CTA walks through `tiles_per_cta` query tiles (rounds of two) with the
 // 160 KB of K / V resident.  The kernel is then MUFU-bound (one ex2 per score).
 //
 //   warp 0      TMA producer: all K / V blocks up front; the Q tile of (round, group) when that group's Q buffer is free
-//   warp 1      MMA issuer:   per key block j:  S_A(j), S_B(j), PV_A(j-1), PV_B(j-1)
+//   warp 1      MMA issuer:   event-driven over both tiles: S(j) when the tile's softmax group has read S(j-1), PV(j) when P(j) is written
 //   warps 2-5   softmax group A, warps 6-9 softmax group B: thread = query row (TMEM lane)
 //   TMEM: group g at columns g*256: S 0..127 | O 128..191 | P 192..255 (fp16 pairs).
 // qkv: [B*N, 3C] fp16 (q | k | v column blocks, head h at column h*64 inside each); out: [B*N, C] fp16.
@@ -103,44 +103,64 @@ vit_attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half* out, int
       // -------------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc_s = umma_idesc_f16in(128, 128, 0);
       constexpr uint32_t idesc_o = umma_idesc_f16in(128, 64, 1);
+      // Event-driven issue: whichever MMA group of either query tile has its operands ready goes next (non-blocking
+      // barrier probes), so the two tiles drift half a block apart and the TMEM loads / stores / barrier hand-offs of one
+      // tile run under the exponentials of the other.  (A static order S_A, S_B, PV_A, PV_B keeps both softmax groups in
+      // the same phase: 2.6 us per key block for the pair instead of ~1.3.)  The second tile's very first S waits until the
+      // first tile's S has been read, which sets the offset.
       for (int r = 0; r < n_rounds; ++r) {
         const int ng = (2 * r + 1 < n_my) ? 2 : 1;       // groups with a tile in this round
-        auto issue_pv = [&](int g, int i) {
-          const int pc = r * nblk + i;                    // PV count of this group
-          mbar_wait(&bars->v_full[i], 0);
-          if (i == 0 && r > 0) mbar_wait(&bars->o_free[g], (r - 1) & 1);   // last round's epilogue has read O
-          mbar_wait(&bars->p_full[g], pc & 1);
-          tc_fence_after();
-          const uint32_t v_addr = smem_u32(kv_tile + (2 * i + 1) * kVit2Tile);
-          const uint32_t tO = tmem_base + static_cast<uint32_t>(g * 256 + 128), tP = tmem_base + static_cast<uint32_t>(g * 256 + 192);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {   // 16 keys per MMA: 8 packed TMEM columns of P
-            const uint64_t db = umma_desc_mn_sw128(v_addr + kk * 16 * 128, kVit2Tile, 1024);
-            umma_f16_ts(tO, tP + static_cast<uint32_t>(kk * 8), db, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(&bars->p_empty[g]);
-        };
         for (int g = 0; g < ng; ++g) mbar_wait(&bars->q_full[g], r & 1);
         tc_fence_after();
-        for (int j = 0; j < nblk; ++j) {
-          mbar_wait(&bars->k_full[j], 0);
+        int js[2] = {0, 0}, jp[2] = {0, 0};
+        uint32_t idle = 0;
+        while (jp[0] < nblk || (ng == 2 && jp[1] < nblk)) {
+          bool progress = false;
           for (int g = 0; g < ng; ++g) {
-            const int sc = r * nblk + j;                  // S count of this group
-            mbar_wait(&bars->s_empty[g], (sc & 1) ^ 1);   // the softmax group has read S(sc - 1)
-            tc_fence_after();
-            const uint32_t q_addr = smem_u32(q_tile + g * kVit2Tile);
-            const uint32_t k_addr = smem_u32(kv_tile + (2 * j) * kVit2Tile);
+            if (jp[g] < js[g]) {                          // PV(jp): S(jp) was issued; needs P(jp), V(jp) (and a free O at block 0)
+              const int i = jp[g], pc = r * nblk + i;
+              if (mbar_test_wait(&bars->p_full[g], pc & 1) && mbar_test_wait(&bars->v_full[i], 0) &&
+                  (i > 0 || r == 0 || mbar_test_wait(&bars->o_free[g], (r - 1) & 1))) {
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(kv_tile + (2 * i + 1) * kVit2Tile);
+                const uint32_t tO = tmem_base + static_cast<uint32_t>(g * 256 + 128), tP = tmem_base + static_cast<uint32_t>(g * 256 + 192);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)                // 16 dims per MMA
-              umma_f16(tmem_base + static_cast<uint32_t>(g * 256), umma_desc_sw128(q_addr + kk * 32), umma_desc_sw128(k_addr + kk * 32),
-                       idesc_s, kk > 0 ? 1u : 0u);
-            umma_commit(&bars->s_full[g]);
-            if (j == nblk - 1) umma_commit(&bars->q_empty[g]);   // every S MMA of the round has retired: Q buffer reusable
+                for (int kk = 0; kk < 8; ++kk) {   // 16 keys per MMA: 8 packed TMEM columns of P
+                  const uint64_t db = umma_desc_mn_sw128(v_addr + kk * 16 * 128, kVit2Tile, 1024);
+                  umma_f16_ts(tO, tP + static_cast<uint32_t>(kk * 8), db, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&bars->p_empty[g]);
+                ++jp[g];
+                progress = true;
+              }
+            }
+            if (js[g] < nblk) {                           // S(js): needs K(js) and the softmax group to have read S(js - 1)
+              const int j = js[g], sc = r * nblk + j;
+              // (js[0] >= 2 implies tile A's first S was read; while js[0] == 1 the parity probe is unambiguous)
+              const bool offset_ok = !(g == 1 && r == 0 && j == 0) || js[0] >= 2 || (js[0] == 1 && mbar_test_wait(&bars->s_empty[0], 0));
+              if (offset_ok && mbar_test_wait(&bars->k_full[j], 0) && mbar_test_wait(&bars->s_empty[g], (sc & 1) ^ 1)) {
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(q_tile + g * kVit2Tile);
+                const uint32_t k_addr = smem_u32(kv_tile + (2 * j) * kVit2Tile);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)            // 16 dims per MMA
+                  umma_f16(tmem_base + static_cast<uint32_t>(g * 256), umma_desc_sw128(q_addr + kk * 32), umma_desc_sw128(k_addr + kk * 32),
+                           idesc_s, kk > 0 ? 1u : 0u);
+                umma_commit(&bars->s_full[g]);
+                if (j == nblk - 1) umma_commit(&bars->q_empty[g]);   // every S MMA of the round has retired: Q buffer reusable
+                ++js[g];
+                progress = true;
+              }
+            }
           }
-          if (j >= 1)
-            for (int g = 0; g < ng; ++g) issue_pv(g, j - 1);
+          if (progress) {
+            idle = 0;
+          } else if (++idle > (1u << (VLO_MBAR_BOUND_LOG2 + 4))) {
+            printf("vlo: vit_attn_tc2 issuer stalled block(%d,%d,%d) round %d S %d/%d PV %d/%d\n", blockIdx.x, blockIdx.y, blockIdx.z, r,
+                   js[0], js[1], jp[0], jp[1]);
+            __trap();
+          }
         }
-        for (int g = 0; g < ng; ++g) issue_pv(g, nblk - 1);
       }
     }
   } else {
