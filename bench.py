@@ -115,7 +115,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU (reference algorithm) arm
-def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 0, vit_layers: int = 0, budget_s: float = 150.0):
+def cpu_reference_times(n_steps: int, n_warm: int, dec_layers: int = 0, vit_layers: int = 0, budget_s: float = 200.0):
     """Times the oracle (CPU port of the reference forward, oracle/vlo_oracle.py) on the host cores.
 
     A step is the FULL frame step (24 ViT blocks + connector, 32 decoder layers over a 12k-token cache, lm_head,
