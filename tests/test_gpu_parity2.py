@@ -536,3 +536,21 @@ def test_offline_encode_directory_on_the_engine(built, tiny, tmp_path):
         ref = O.siglip_vision_encode(vis, cfg, read_video_resampled(str(src / f"{name}.avi")))
         mx, frac = _close(feats, ref, 3e-2 + 8e-3, 2e-2)             # VIT_ATOL + one bf16 ulp of O(1) tokens
         assert frac == 0.0, (name, mx)
+
+
+# ------------------------------------------------------------------------------------------- alternative kernel generations
+@pytest.mark.parametrize("env", ["VLO_FUSE=15", "VLO_FUSE=0", "VLO_ATTN=3", "VLO_ATTN=1", "VLO_VIT_ATTN=2 VLO_VIT_SMALL_BN=64", "VLO_VIT_ATTN=3"])
+def test_non_default_kernel_paths_keep_parity(env):
+    """The kernel generations that are not the measured-best default stay selectable (A/B switches, read once per process):
+    fused stream-K finishers (all four / none; the default fuses gate|up only), the decoder attention generations 3 (P in TMEM) and 1
+    (mma.sync), the one-tile tcgen05 ViT attention with 64-token co-resident tiles, the two-tile ViT attention at batch 1.
+    Each runs the reference-golden parity tests of the tiny model in its own process."""
+    import os
+    import subprocess
+    e = dict(os.environ)
+    for kv in env.split():
+        k, v = kv.split("=")
+        e[k] = v
+    r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "chunked or greedy or vit_tokens or batched or state_machine"], env=e, capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-500:]

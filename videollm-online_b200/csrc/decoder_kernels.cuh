@@ -207,12 +207,11 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const SwigluParams p) {
   const long long n4 = static_cast<long long>(p.T) * p.I / 4;
   const long long idx0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   // index arithmetic and stream-K plane counts of the first element group: before the grid dependency resolves
-  int t0 = 0, c0 = 0, ng0 = 0, nu0 = 0;
+  int t0 = 0, c0 = 0, ng0 = 0;
   if (idx0 < n4) {
     const long long e = idx0 * 4;
     t0 = static_cast<int>(e / p.I), c0 = static_cast<int>(e % p.I);
     ng0 = p.n_splits > 0 ? p.n_splits : sk_planes(c0 >> 6, p.sk);
-    nu0 = ng0;
   }
   pdl_wait();
   for (long long idx = idx0; idx < n4; idx += static_cast<long long>(gridDim.x) * blockDim.x) {

@@ -167,17 +167,21 @@ int gemm_partial(vlo_engine* e, const bf16* w, int n_out, const bf16* x, int T, 
   return gemm_ws_launch(c, st);
 }
 
-// Fused-finisher switch (VLO_FUSE=1; default off).  Same-box A/B (tools/gpu_r2_call7.sh): the fused chain (8 launches per
-// layer) runs the frame step at 192 frames/s, planes + separate fix-up kernels (10 launches) at 201: a finisher's epilogue
-// (flag acquire -> plane loads -> RoPE table loads -> stores) is a ~3 us tail at the end of EVERY CTA during which the SM
-// streams nothing, while a separate fix-up kernel runs next to the next GEMM's CTA, whose ring is already filling.
-bool fuse_enabled() {
+// Which stream-K fix-ups run inside the GEMM's finisher CTAs (gemm_wsf.cuh) instead of a separate kernel.  A finisher's
+// epilogue (flag acquire -> plane loads -> table loads -> stores) is a ~3 us tail at the end of EVERY CTA during which its SM
+// streams nothing, while a separate fix-up kernel runs next to the next GEMM's CTA, whose ring is already filling: fusing all
+// four is slower than fusing none.
+// VLO_FUSE bit mask: 1 = q|k|v (+RoPE +append), 2 = o_proj (+residual), 4 = gate|up (+SwiGLU), 8 = down_proj (+residual);
+// "all" = 15.  Default 4, by measurement (tools/gpu_r2_call18.sh, decoder frame step alone at 12k, ms): 0 -> 4.14, 15 -> 4.47,
+// 1 -> 4.39, 2 -> 4.32, 4 -> 3.98, 8 -> 4.30, 5 -> 4.18, 10 -> 4.46.  Only the gate|up GEMM gains: it is the one with enough
+// tiles (224, 1.5 per CTA) to amortise the finisher's tail, and fusing it removes the 3.6 MB plane round trip of its fix-up.
+int fuse_mask() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VLO_FUSE");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    v = (e == nullptr) ? 4 : ((e[0] == 'a') ? 15 : (atoi(e) & 15));
   }
-  return v == 1;
+  return v;
 }
 
 // stream-K GEMM whose finisher CTAs apply the fix-up themselves (gemm_wsf.cuh); `a` carries the epilogue's operands
@@ -997,8 +1001,11 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
     const DecLayer& d = e->dec[l];
     SkInfo sk{};
     const bool is_last = (l == c.num_layers - 1);
-    if (fuse_enabled()) {
-      // 8 launches per layer: the stream-K finisher CTAs apply RoPE + KV append / residual add / SwiGLU themselves
+    const int fm = fuse_mask();
+    GemmWsfArgs r{};
+    r.h = e->h;
+    // ---- q|k|v projection (+ RoPE + in-place KV append): fused finisher, or planes + fix-up kernel
+    if (fm & 1) {
       GemmWsfArgs a{};
       a.cos_tab = e->rope_cos;
       a.sin_tab = e->rope_sin;
@@ -1011,24 +1018,8 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
       a.n_heads = c.num_heads;
       a.n_kv_heads = c.num_kv_heads;
       if (gemm_fused(e, a, WSF_QKV, d.qkv, e->qkv_width, e->xn, T, H, st)) return -1;
-      if (attn_run(plan, e->q, kv_layer_base(e, l, 0), kv_layer_base(e, l, 1), kv_rows_per_layer(c), e->attn_out,
-                   c.num_heads, c.num_kv_heads, c.head_dim, st))
-        return -1;
-      GemmWsfArgs r{};
-      r.h = e->h;
-      if (gemm_fused(e, r, WSF_RESID, d.o, H, e->attn_out, T, attn_width, st)) return -1;
-      if (resid_norm(nullptr, 0, d.post_norm, false)) return -1;
-      GemmWsfArgs g{};
-      g.act = e->act;
-      g.I = c.intermediate_size;
-      if (gemm_fused(e, g, WSF_SWIGLU, d.gate_up, 2 * c.intermediate_size, e->xn, T, H, st)) return -1;
-      if (gemm_fused(e, r, WSF_RESID, d.down, H, e->act, T, c.intermediate_size, st)) return -1;
-      if (resid_norm(nullptr, 0, is_last ? e->final_norm : e->dec[l + 1].in_norm, is_last)) return -1;
-      continue;
-    }
-    // fused q|k|v projection -> partials; fix-up + RoPE + in-place KV append
-    if (gemm_partial(e, d.qkv, e->qkv_width, e->xn, T, H, &sk, st)) return -1;
-    {
+    } else {
+      if (gemm_partial(e, d.qkv, e->qkv_width, e->xn, T, H, &sk, st)) return -1;
       QkvRopeParams p{};
       p.part = e->part;
       p.n_splits = -1;
@@ -1050,10 +1041,22 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
     if (attn_run(plan, e->q, kv_layer_base(e, l, 0), kv_layer_base(e, l, 1), kv_rows_per_layer(c), e->attn_out,
                  c.num_heads, c.num_kv_heads, c.head_dim, st))
       return -1;
-    if (gemm_partial(e, d.o, H, e->attn_out, T, attn_width, &sk, st)) return -1;
-    if (resid_norm(&sk, static_cast<long long>(T) * H, d.post_norm, false)) return -1;
-    if (gemm_partial(e, d.gate_up, 2 * c.intermediate_size, e->xn, T, H, &sk, st)) return -1;
-    {
+    // ---- o_proj + residual, then post-attention RMSNorm
+    if (fm & 2) {
+      if (gemm_fused(e, r, WSF_RESID, d.o, H, e->attn_out, T, attn_width, st)) return -1;
+      if (resid_norm(nullptr, 0, d.post_norm, false)) return -1;
+    } else {
+      if (gemm_partial(e, d.o, H, e->attn_out, T, attn_width, &sk, st)) return -1;
+      if (resid_norm(&sk, static_cast<long long>(T) * H, d.post_norm, false)) return -1;
+    }
+    // ---- gate|up + SwiGLU
+    if (fm & 4) {
+      GemmWsfArgs g{};
+      g.act = e->act;
+      g.I = c.intermediate_size;
+      if (gemm_fused(e, g, WSF_SWIGLU, d.gate_up, 2 * c.intermediate_size, e->xn, T, H, st)) return -1;
+    } else {
+      if (gemm_partial(e, d.gate_up, 2 * c.intermediate_size, e->xn, T, H, &sk, st)) return -1;
       SwigluParams p{};
       p.part = e->part;
       p.n_splits = -1;
@@ -1067,8 +1070,15 @@ int vlo_step_ids(vlo_engine* e, int n_seqs, const int32_t* h_stream_ids, const i
                           dim3(256), 0, st, p));
       count_launch();
     }
-    if (gemm_partial(e, d.down, H, e->act, T, c.intermediate_size, &sk, st)) return -1;
-    if (resid_norm(&sk, static_cast<long long>(T) * H, is_last ? e->final_norm : e->dec[l + 1].in_norm, is_last)) return -1;
+    // ---- down_proj + residual, then the next RMSNorm (next layer's input norm, or the final norm + last-row compaction)
+    const bf16* next_norm = is_last ? e->final_norm : e->dec[l + 1].in_norm;
+    if (fm & 8) {
+      if (gemm_fused(e, r, WSF_RESID, d.down, H, e->act, T, c.intermediate_size, st)) return -1;
+      if (resid_norm(nullptr, 0, next_norm, is_last)) return -1;
+    } else {
+      if (gemm_partial(e, d.down, H, e->act, T, c.intermediate_size, &sk, st)) return -1;
+      if (resid_norm(&sk, static_cast<long long>(T) * H, next_norm, is_last)) return -1;
+    }
   }
   // ---- last-position lm_head + on-device decision
   bf16* logits = d_last_logits ? static_cast<bf16*>(d_last_logits) : e->logits;
