@@ -40,16 +40,8 @@ int attn_version_impl(int G, int max_kv_len = 0) {
   if (forced > 0) return forced;
   return max_kv_len >= 24576 ? 3 : 2;
 }
-// keys per pipeline block of the v3 kernel (VLO_ATTN_BLK=64|128)
-int attn_tc2_blk() {
-  static int blk = 0;
-  if (blk == 0) {
-    const char* e = getenv("VLO_ATTN_BLK");
-    (void)e;   // 64-key blocks were measured slower (per-block latency dominates): the kernel is built for 128
-    blk = 128;
-  }
-  return blk;
-}
+// keys per pipeline block of the generation-3 kernel (64-key blocks were measured slower: per-block latency dominates)
+int attn_tc2_blk() { return 128; }
 size_t max_ctas(int total_tokens, int n_seqs, int n_heads, int n_kv_heads) {
   return static_cast<size_t>(kNumSMs) + static_cast<size_t>(n_kv_heads) * max_chunks(total_tokens, n_seqs, n_heads / n_kv_heads);
 }
@@ -288,14 +280,9 @@ static int attn_run_tc(const AttnPlan& plan, const void* d_q, const void* d_k, c
   p.base.n_kv_heads = n_kv_heads;
   p.base.scale_log2 = scale_log2;
   // V tile = MN-major B operand: 64-d halves 16 KB apart (LBO), 8-key groups 1 KB apart (SBO)
-  static int swap_ls = -1;
-  if (swap_ls < 0) {
-    const char* e = getenv("VLO_ATTN_VDESC");
-    swap_ls = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
   p.dbg = attn_trace_buffer_for_launch();
-  p.v_lbo = swap_ls ? 1024u : static_cast<uint32_t>(kTcSub);
-  p.v_sbo = swap_ls ? static_cast<uint32_t>(kTcSub) : 1024u;
+  p.v_lbo = static_cast<uint32_t>(kTcSub);
+  p.v_sbo = 1024u;
   prof_begin(PROF_ATTN, stream, plan.algo_bytes);
   VLO_CUDA(launch_pdl(attn_tc_kernel, dim3(plan.max_splits, n_kv_heads, plan.n_items), dim3(kTcThreads), kTcSmemBytes, stream,
                       tk, tv, tq, p));
