@@ -374,17 +374,21 @@ int gemm_wsf_launch(const GemmWsfArgs& a, const void* w, const void* x, int epi,
   if (get_tmap(w, a.rows_w, a.k, kGemmBM, FMT_BF16, &tw) != 0) return -1;
   if (get_tmap(x, a.rows_x, a.k, bn, FMT_BF16, &tx) != 0) return -1;
   if (bn == 16) {
-    // ring depth (VLO_WSF_STAGES=4|5|6).  6 x 18 KB + the 8.7 KB exchange tile = 118 KB: ONE such CTA per SM.  5 stages = 100 KB:
-    // the next GEMM of the chain becomes resident beside this one and fills its ring during this one's main loop and
-    // finisher tail.
+    // ring depth (VLO_WSF_STAGES=4|5|6|8|10; default 8 = 144 KB + the 8.7 KB exchange tile).  Same-box A/Bs: the decoder step
+    // alone does not care (3.97-3.99 ms for 6 / 8 / 10 stages; 5 and 4 stages, which let the next GEMM's CTA become resident
+    // beside this one, are slower: 4.02 / 4.07); next to the co-resident ViT 8 stages measure 211 vs 208 frames/s - the ViT's
+    // CTAs then cannot share an SM with the (only) fused GEMM, gate|up, and stop competing with its stream.
     static int st = 0;
     if (st == 0) {
       const char* e = getenv("VLO_WSF_STAGES");
-      st = e ? atoi(e) : 6;
+      st = e ? atoi(e) : 8;
     }
     if (st == 4) return launch_wsf_epi<16, 4>(epi, tw, tx, a, stream);
     if (st == 5) return launch_wsf_epi<16, 5>(epi, tw, tx, a, stream);
-    return launch_wsf_epi<16, 6>(epi, tw, tx, a, stream);
+    if (st == 8) return launch_wsf_epi<16, 8>(epi, tw, tx, a, stream);
+    if (st == 10) return launch_wsf_epi<16, 10>(epi, tw, tx, a, stream);
+    if (st == 6) return launch_wsf_epi<16, 6>(epi, tw, tx, a, stream);
+    return launch_wsf_epi<16, 8>(epi, tw, tx, a, stream);
   }
   if (bn == 32) return launch_wsf_epi<32, ws_default_stages(32)>(epi, tw, tx, a, stream);
   if (bn == 64) return launch_wsf_epi<64, ws_default_stages(64)>(epi, tw, tx, a, stream);
