@@ -8,13 +8,15 @@
 // memory.  Per 64-wide k-block a CTA pulls 16 KB of X + 16 KB of W (BN = 256) for 4.2 MFLOP: half the L2 -> SM bytes per
 // flop of the 128 x 192 single-CTA tiles this replaces, which is what bounds a 1.5 PFLOP/s tensor core fed from L2.
 //
-//   warp 0      TMA producer (both CTAs): X box [128 x 64], W box [BN/2 x 64], 128B-swizzled, 6 (8) stages;
+//   warp 0      TMA producer (both CTAs): X box [128 x 64], W box [BN/2 x 64], 128B-swizzled, 5 (BN = 256) / 7 (BN = 128) stages;
 //               cp.async.bulk.tensor...cta_group::2 signals the LEADER CTA's full barrier for both CTAs' bytes
 //   warp 1      TMEM allocation (cta_group::2, both CTAs); in the leader CTA one thread issues tcgen05.mma.cta_group::2
 //               and commits with .multicast::cluster to the empty / accumulator-full barriers of BOTH CTAs
-//   warps 2-5   epilogue (both CTAs): tcgen05.ld 32 columns of the own token row -> bias / activation / fp16 (or the
-//               fp32 residual add) -> 64-byte vector stores; two accumulator buffers: the epilogue of tile i overlaps the
-//               MMAs of tile i + 1.  Persistent: pair p runs tiles p, p + n_pairs, ...
+//   warps 2-5   epilogue (both CTAs): tcgen05.ld 32 columns of the own token row -> bias / activation / rounding -> a
+//               128B-swizzled 16 KB panel in shared memory (two, ping-pong) -> TMA store (fp16) or TMA reduce-add (fp32
+//               residual stream); two accumulator buffers: the epilogue of tile i overlaps the MMAs of tile i + 1.
+//               Persistent: pair p runs tiles p, p + n_pairs, ...
+// PDL: launched with the programmatic attribute, but it never triggers its successor early (gemm.cu: VLO_GEMM2_PDL).
 // Replaces for the ViT the cuBLAS GEMMs reached from HF:models/siglip/modeling_siglip.py:285-287 (q/k/v), 309 (out_proj),
 // 323-327 (fc1 + gelu_pytorch_tanh, fc2).
 #pragma once
