@@ -481,7 +481,8 @@ def run_engine_arm(args):
                 cls[nm] = {"launches_per_step": n[j] / P, "ms_per_step": ms[j] / P, "avg_us_per_launch": 1e3 * ms[j] / n[j],
                            "algo_gb_per_step": by[j] / P / 1e9, "achieved_gbs": (by[j] / 1e9) / (ms[j] / 1e3) if ms[j] > 0 else None}
         gs, at = cls.get("gemm_weight_stream"), cls.get("attn_kvappend")
-        roof = {"bound": "hbm", "kernel": "gemm_ws_kernel<bf16> (persistent stream-K weight streaming: 14.0 GB of the 16.6 GB/step)",
+        roof = {"bound": "hbm", "kernel": "gemm_ws_kernel<bf16> / gemm_wsf_kernel (persistent stream-K weight streaming, same mainloop; 14.0 GB of the 16.6 GB/step; "
+                          "the micro-loop runs the plain stream-K form of all four GEMMs of a layer, the step fuses the gate|up fix-up)",
                 "achieved": micro_gemm["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": micro_gemm["achieved_gbs"] / hbm_peak,
                 "peak_source": which, "traffic": _ncu_traffic("gemm_ws_decoder")[0], "traffic_commit": _ncu_traffic("gemm_ws_decoder")[1],
                 "avg_us_per_launch": micro_gemm["us_per_launch"], "algo_bytes_per_launch": micro_gemm["algo_bytes_per_launch"],
