@@ -273,6 +273,27 @@ def test_video_ingest_matches_ffmpeg_once_geometry(tmp_path):
         read_video_resampled(str(tmp_path / "missing.mp4"))
 
 
+def test_video_ingest_of_the_reference_demo_clips():
+    """The clips demo/cli.py:12 plays (demo/assets/cooking.mp4 1440x1080, bicycle.mp4 512x384, 30 fps, ~100 s): streamed
+    through the ingest at the demo's 2 FPS / 384 px.  Build container only (the reference checkout does not travel)."""
+    pytest.importorskip("cv2")
+    import os
+    from videollm_online_b200.video_ingest import letterbox_geometry, read_video_resampled
+    root = os.path.join(os.environ.get("VLO_REFERENCE", "/root/reference"), "demo", "assets")
+    if not os.path.isfile(os.path.join(root, "cooking.mp4")):
+        pytest.skip("reference demo assets not present")
+    for name, (w, h, n_src) in {"cooking.mp4": (1440, 1080, 3204), "bicycle.mp4": (512, 384, 3000)}.items():
+        v = read_video_resampled(os.path.join(root, name), fps=2, resolution=384)
+        n_out = round(n_src / 30.0 * 2)
+        assert v.dtype == torch.uint8 and tuple(v.shape) == (n_out, 3, 384, 384), (name, tuple(v.shape))
+        sw, sh, x0, y0 = letterbox_geometry(w, h, 384)
+        assert (sw, sh, x0, y0) == (384, 288, 0, 48)
+        assert int(v[:, :, :y0].max()) == 0 and int(v[:, :, y0 + sh:].max()) == 0         # black bars of the pad filter
+        band = v[:, :, y0:y0 + sh].float()
+        assert band.mean() > 30 and band.std() > 20                                         # a real picture in between
+        assert (v[0].float() - v[-1].float()).abs().mean() > 2                              # and it changes over the clip
+
+
 def test_offline_encode_directory_layout_and_sharding(tmp_path, tiny):
     """the host loop of distributed_encode (data/utils.py:86-104) - clip -> batches -> tokens -> .pt,
     round-robin over ranks - driven here with the CPU oracle's SigLIP encode as the `vision_encode` callable."""
