@@ -76,6 +76,8 @@ run(256, 128, 128, 0, 0, 128, time_it=False)
 run(200, 256, 256, 0, 0, 256, time_it=False)       # ragged rows inside the peer half
 run(700, 512, 1024, 0, 1, 256, time_it=False)      # peer half fully out of range on the last token tile; several tiles per pair
 run(1728, 1024, 1024, 1, 0, 128, time_it=False)    # B = 3: residual epilogue
+run(2880, 1024, 1024, 1, 0, 128, time_it=False)    # B = 5: the peer CTA's half of the last token tile starts past the matrix
+run(2880, 3072, 1024, 0, 0, 256, time_it=False)
 for B in (4, 8):
     R = 576 * B
     run(R, 3072, 1024, 0, 0, 256)     # q|k|v

@@ -175,8 +175,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       int i = 0;
       for (int t = pair; t < tiles; t += n_pairs) {
         const int mt = t % p.m_tiles, nt = t / p.m_tiles;
-        const int row_x = mt * 256 + static_cast<int>(rank) * 128;
-        const int row_w = nt * BN + static_cast<int>(rank) * (BN / 2);
+        // a half tile that starts past the end of its matrix (token count mod 256 in 1..128: 5, 9, 13 ... frames) loads
+        // from the last valid row instead of issuing a fully out-of-range box; its results are never stored (the TMA store
+        // clips rows >= rows_x / columns >= rows_w)
+        const int row_x = min(mt * 256 + static_cast<int>(rank) * 128, p.rows_x - 1);
+        const int row_w = min(nt * BN + static_cast<int>(rank) * (BN / 2), p.rows_w - 1);
         for (int j = 0; j < kb; ++j, ++i) {
           const int s = i % S;
           const uint32_t ph = (i / S) & 1;
@@ -283,8 +286,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         fence_proxy_async();      // generic-proxy writes -> visible to the async proxy (TMA)
         g2_epi_sync();
         if (store_thread) {
-          if (EPI == G2_STORE16) tma_store_2d(&tm_out, smem_out + pbuf * Cfg::kStoreBytes, nt * BN + c0, row0);
-          else tma_reduce_add_2d(&tm_out, smem_out + pbuf * Cfg::kStoreBytes, nt * BN + c0, row0);
+          if (row0 < p.rows_x && nt * BN + c0 < p.rows_w) {   // (a panel entirely outside the matrix is not issued at all)
+            if (EPI == G2_STORE16) tma_store_2d(&tm_out, smem_out + pbuf * Cfg::kStoreBytes, nt * BN + c0, row0);
+            else tma_reduce_add_2d(&tm_out, smem_out + pbuf * Cfg::kStoreBytes, nt * BN + c0, row0);
+          }
           bulk_commit_group();
         }
       }
